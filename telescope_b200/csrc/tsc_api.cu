@@ -1,0 +1,1051 @@
+// libtelescope_b200.so -- host orchestration and C ABI (include/telescope_b200.h).
+//
+// Replaces, behind a C ABI, TelescopeLikelihood (reference telescope/utils/model.py:631-865) and the
+// csr_matrix_plus helpers it calls (telescope/utils/sparse_plus.py:16-165).  No CPU fallback: every compute entry
+// point needs a CUDA device and fails loudly otherwise.
+//
+// Layout in HBM, per shard (= one GPU's contiguous block of reads):
+//   q[nnz] fp64, col[nnz] int32 (internal locus numbering: descending entry count, so hot loci are low indices),
+//   indptr[rows+1] int64, wy[rows] fp64 (= w_i * Y_i), tiles[~nnz/115] 32-byte descriptors for the fused kernel,
+//   and K-length fp64 vectors: pi, theta, pt (= pi*theta), their *_prev twins (the parameters the stored posterior
+//   z was computed from, model.py:795), *_init, pisum0, thetasum, R accumulator replicas.
+// Per EM iteration and shard: fused E+M kernel -> replica reduce -> [NCCL all-reduce of K doubles] -> update kernel.
+// The loop runs ahead of the host; convergence is decided on the device and polled through pinned memory.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <functional>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <nccl.h>   // types and prototypes only; the library is dlopen'ed (tsc_set_nccl_path)
+
+#include "../../include/telescope_b200.h"
+#include "tsc_kernels.cuh"
+#include "tsc_tiles.cuh"
+
+using namespace tsc;
+
+// ------------------------------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(TSC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                          std::to_string(__LINE__) + ")");                            \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------- NCCL (dlopen)
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static std::string g_nccl_path;
+
+static int nccl_load() {
+    if (g_nccl.lib) return TSC_OK;
+    std::vector<std::string> cands;
+    if (!g_nccl_path.empty()) cands.push_back(g_nccl_path);
+    if (const char* e = getenv("TELESCOPE_B200_NCCL")) cands.push_back(e);
+    cands.push_back("libnccl.so.2");
+    cands.push_back("libnccl.so");
+    std::string tried;
+    for (auto& c : cands) {
+        void* lib = dlopen(c.c_str(), RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { tried += c + " (" + (dlerror() ? "not loadable" : "?") + "); "; continue; }
+        NcclApi a; a.lib = lib;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(lib, "ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(lib, "ncclCommDestroy");
+        a.AllReduce = (decltype(a.AllReduce))dlsym(lib, "ncclAllReduce");
+        a.GroupStart = (decltype(a.GroupStart))dlsym(lib, "ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd))dlsym(lib, "ncclGroupEnd");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.GroupStart && a.GroupEnd && a.GetErrorString) {
+            g_nccl = a;
+            return TSC_OK;
+        }
+        tried += c + " (symbols missing); ";
+        dlclose(lib);
+    }
+    return fail(TSC_ERR_NCCL, "cannot load NCCL: " + tried);
+}
+
+#define NC(x)                                                                                         \
+    do {                                                                                              \
+        ncclResult_t r_ = (x);                                                                        \
+        if (r_ != ncclSuccess)                                                                        \
+            return fail(TSC_ERR_NCCL, std::string(#x) + ": " + g_nccl.GetErrorString(r_) + " (" + __FILE__ + ":" + \
+                                          std::to_string(__LINE__) + ")");                            \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------- handle
+struct Shard {
+    int dev = 0;
+    int world_rank = 0;
+    cudaStream_t stream = nullptr;
+    long long n_rows = 0, nnz = 0;
+    long long row_begin = 0, nnz_begin = 0;   // within this process's (compacted) reads / entries
+    long long* indptr = nullptr;
+    int* col = nullptr;
+    double* q = nullptr;
+    double* wy = nullptr;
+    Tile* tiles = nullptr;
+    long long n_tiles = 0, n_long = 0;
+    // K-vectors
+    double *pi = nullptr, *theta = nullptr, *pt = nullptr, *pi_prev = nullptr, *theta_prev = nullptr, *pt_prev = nullptr;
+    double *pi_init = nullptr, *theta_init = nullptr, *pisum0 = nullptr, *acc = nullptr, *thetasum = nullptr;
+    double *ones = nullptr, *tmp_a = nullptr, *tmp_b = nullptr, *tmp_c = nullptr, *colsum = nullptr;
+    int* perm = nullptr;      // original -> internal locus index (nullptr = identity)
+    Consts* consts = nullptr;
+    EmState* st = nullptr;
+    EmState* st_host = nullptr;    // pinned, 2 slots
+    double* diffs = nullptr;
+    double* lnls = nullptr;
+    int diffs_cap = 0;
+    double* partials = nullptr;    // per-block partial sums (lnl)
+    double* scalars = nullptr;     // [0..3] init partials / lnl
+    int* bad = nullptr;
+    ncclComm_t comm = nullptr;
+    cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_k;   // 2 per iteration, shard 0 only
+    int n_sm = 0;
+    int grid_rows = 0, grid_tiles = 0;
+    size_t smem_tiles = 0;
+    int s_cols = 0;
+};
+
+struct tsc_handle {
+    std::vector<Shard> shards;
+    int K = 0, world = 1, n_procs = 1, proc_rank = 0;
+    int R = 8, G = 8, kernel = TSC_KERNEL_TILES;
+    bool smem_tab = false;
+    long long n_rows_user = 0, n_rows = 0, nnz = 0;
+    std::vector<long long> rowmap;        // compacted read -> caller's read index (empty when no empty reads)
+    std::vector<int> perm, inv;           // perm[original] = internal; inv[internal] = original
+    Consts consts{};
+    std::vector<double> pisum0_host;
+    bool em_done = false;
+    int n_iter = 0, converged = 0;
+    double lnl = std::numeric_limits<double>::infinity();
+    std::vector<float> kernel_ms;
+    long long launches = 0, h2d = 0, d2h = 0;
+};
+
+#define LAUNCH(h) ((h)->launches++)
+
+static inline int grid_for(long long work, int threads, int cap) {
+    long long b = (work + threads - 1) / threads;
+    return (int)std::max<long long>(1, std::min<long long>(b, cap));
+}
+
+static int allreduce(tsc_handle* h, size_t off_bytes_unused, void* (*ptr_of)(Shard&), size_t count, ncclDataType_t dt, ncclRedOp_t op) {
+    (void)off_bytes_unused;
+    if (h->world == 1) return TSC_OK;
+    NC(g_nccl.GroupStart());
+    for (auto& s : h->shards) {
+        CU(cudaSetDevice(s.dev));
+        void* p = ptr_of(s);
+        NC(g_nccl.AllReduce(p, p, count, dt, op, s.comm, s.stream));
+    }
+    NC(g_nccl.GroupEnd());
+    return TSC_OK;
+}
+#define ALLREDUCE(h, member_expr, count, dt, op)                                                   \
+    do {                                                                                           \
+        int rc_ = allreduce((h), 0, [](Shard& s) -> void* { return (void*)(member_expr); }, (count), (dt), (op)); \
+        if (rc_) return rc_;                                                                       \
+    } while (0)
+
+static int sync_all(tsc_handle* h) {
+    for (auto& s : h->shards) { CU(cudaSetDevice(s.dev)); CU(cudaStreamSynchronize(s.stream)); }
+    return TSC_OK;
+}
+
+// K-vector in the caller's locus numbering -> device (internal numbering), and back
+static int put_kvec(tsc_handle* h, Shard& s, const double* host, double* dev) {
+    std::vector<double> tmp(h->K);
+    for (int j = 0; j < h->K; ++j) tmp[h->perm[j]] = host[j];
+    CU(cudaMemcpyAsync(dev, tmp.data(), sizeof(double) * h->K, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    h->h2d += sizeof(double) * h->K;
+    return TSC_OK;
+}
+static int get_kvec(tsc_handle* h, Shard& s, const double* dev, double* host) {
+    std::vector<double> tmp(h->K);
+    CU(cudaMemcpyAsync(tmp.data(), dev, sizeof(double) * h->K, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    for (int j = 0; j < h->K; ++j) host[j] = tmp[h->perm[j]];
+    h->d2h += sizeof(double) * h->K;
+    return TSC_OK;
+}
+
+template <class F>
+static int launch_rows(int G, F&& f) {
+    switch (G) {
+        case 4: f(std::integral_constant<int, 4>()); break;
+        case 8: f(std::integral_constant<int, 8>()); break;
+        case 16: f(std::integral_constant<int, 16>()); break;
+        default: f(std::integral_constant<int, 32>()); break;
+    }
+    return TSC_OK;
+}
+
+static Csr csr_of(const Shard& s) { return Csr{s.indptr, s.col, s.q, s.n_rows}; }
+
+// ------------------------------------------------------------------------------------------------- tiling
+static void build_tiles(const long long* ip, long long n_rows, std::vector<Tile>& out, long long& n_long) {
+    out.clear();
+    n_long = 0;
+    out.reserve((size_t)(ip[n_rows] / 100 + 16));
+    long long r = 0;
+    while (r < n_rows) {
+        const long long lo = ip[r];
+        const long long base = lo & ~3LL;
+        const int first = (int)(lo - base);
+        Tile t;
+        t.base = base;
+        t.row0 = (int)r;
+        t.flags[0] = t.flags[1] = t.flags[2] = t.flags[3] = 0;
+        if (ip[r + 1] - base > 128) {   // long read
+            const long long len = ip[r + 1] - lo;
+            t.meta = (first << 8) | (1 << 16);
+            t.flags[0] = (unsigned)(len & 0xffffffffLL);
+            t.flags[1] = (unsigned)(len >> 32);
+            out.push_back(t);
+            ++n_long;
+            ++r;
+            continue;
+        }
+        long long r2 = r;
+        while (r2 < n_rows && ip[r2 + 1] - base <= 128 && (r2 - r) < 128) {
+            const int p = (int)(ip[r2] - base);
+            t.flags[p >> 5] |= 1u << (p & 31);
+            ++r2;
+        }
+        const int end = (int)(ip[r2] - base);
+        if (end < 128) t.flags[end >> 5] |= 1u << (end & 31);
+        t.meta = (end & 0xff) | (first << 8) | ((int)(r2 - r) << 16);
+        out.push_back(t);
+        r = r2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- small API
+extern "C" int tsc_abi_version(void) { return TSC_ABI_VERSION; }
+extern "C" const char* tsc_last_error(void) { return g_err.c_str(); }
+
+extern "C" int tsc_device_count(int32_t* n_out) {
+    if (!n_out) return fail(TSC_ERR_ARG, "n_out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *n_out = 0; return fail(TSC_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *n_out = n;
+    return TSC_OK;
+}
+
+extern "C" int tsc_set_nccl_path(const char* path) {
+    g_nccl_path = path ? path : "";
+    return TSC_OK;
+}
+
+extern "C" int tsc_nccl_unique_id(void* out128) {
+    if (!out128) return fail(TSC_ERR_ARG, "out128 is NULL");
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return TSC_OK;
+}
+
+extern "C" void tsc_config_default(tsc_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->n_local_devices = 1;
+    cfg->n_procs = 1;
+    cfg->kernel = TSC_KERNEL_AUTO;
+    cfg->replicas = 0;
+    cfg->smem_table_cols = -1;
+    cfg->smem_acc_cols = -1;
+    cfg->permute_columns = 1;
+}
+
+static void free_shard(Shard& s) {
+    cudaSetDevice(s.dev);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    void* ptrs[] = {s.indptr, s.col, s.q, s.wy, s.tiles, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
+                    s.pi_init, s.theta_init, s.pisum0, s.acc, s.thetasum, s.ones, s.tmp_a, s.tmp_b, s.tmp_c, s.colsum,
+                    s.perm, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (s.st_host) cudaFreeHost(s.st_host);
+    for (auto& e : s.ev_poll) if (e) cudaEventDestroy(e);
+    for (auto& e : s.ev_k) if (e) cudaEventDestroy(e);
+    if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Shard();
+}
+
+extern "C" void tsc_destroy(tsc_handle* h) {
+    if (!h) return;
+    for (auto& s : h->shards) free_shard(s);
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------------------- create
+static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user, int32_t n_cols, int64_t nnz,
+                       const void* indptr, int32_t indptr_bytes, const int32_t* indices, const uint16_t* raw,
+                       const double* q_lut, int32_t lut_len, double pi_prior, double theta_prior) {
+    const int K = n_cols;
+    h->K = K;
+    h->n_rows_user = n_rows_user;
+    h->nnz = nnz;
+    h->n_procs = std::max(1, cfg.n_procs);
+    h->proc_rank = cfg.proc_rank;
+    const int n_local = std::max(1, cfg.n_local_devices);
+    h->world = h->n_procs * n_local;
+    if (h->n_procs > 1 && !cfg.nccl_id) return fail(TSC_ERR_ARG, "n_procs > 1 needs nccl_id");
+    if (h->proc_rank < 0 || h->proc_rank >= h->n_procs) return fail(TSC_ERR_ARG, "proc_rank out of range");
+
+    int ndev = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            return fail(TSC_ERR_CUDA, std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                                          "); telescope_b200 has no CPU fallback");
+    }
+    for (int i = 0; i < n_local; ++i) {
+        const int d = cfg.device_ids ? cfg.device_ids[i] : i;
+        if (d < 0 || d >= ndev) return fail(TSC_ERR_ARG, "device id " + std::to_string(d) + " not present");
+    }
+
+    // ---- read pointers: int64 copy, validation, empty-read compaction
+    std::vector<long long> ip((size_t)n_rows_user + 1);
+    if (indptr_bytes == 4) { const int32_t* p = (const int32_t*)indptr; for (int64_t i = 0; i <= n_rows_user; ++i) ip[i] = p[i]; }
+    else { const int64_t* p = (const int64_t*)indptr; for (int64_t i = 0; i <= n_rows_user; ++i) ip[i] = p[i]; }
+    if (ip[0] != 0 || ip[n_rows_user] != nnz) return fail(TSC_ERR_ARG, "indptr[0] must be 0 and indptr[n_rows] must be nnz");
+    bool has_empty = false;
+    for (int64_t i = 0; i < n_rows_user; ++i) {
+        if (ip[i + 1] < ip[i]) return fail(TSC_ERR_ARG, "indptr is not non-decreasing");
+        if (ip[i + 1] == ip[i]) has_empty = true;
+    }
+    if (has_empty) {
+        h->rowmap.reserve(n_rows_user);
+        std::vector<long long> ip2;
+        ip2.reserve(n_rows_user + 1);
+        ip2.push_back(0);
+        for (int64_t i = 0; i < n_rows_user; ++i)
+            if (ip[i + 1] > ip[i]) { h->rowmap.push_back(i); ip2.push_back(ip[i + 1]); }
+        ip.swap(ip2);
+    }
+    const long long n_rows = (long long)ip.size() - 1;
+    h->n_rows = n_rows;
+
+    // ---- shard boundaries: contiguous, balanced by entry count
+    std::vector<long long> rb(n_local + 1, 0);
+    rb[n_local] = n_rows;
+    for (int i = 1; i < n_local; ++i) {
+        const long long target = nnz / n_local * i;
+        rb[i] = std::lower_bound(ip.begin(), ip.end(), target) - ip.begin();
+        rb[i] = std::min(std::max(rb[i], rb[i - 1]), n_rows);
+    }
+
+    // ---- NCCL
+    ncclUniqueId id;
+    if (h->world > 1) {
+        int rc = nccl_load();
+        if (rc) return rc;
+        if (h->n_procs > 1) memcpy(&id, cfg.nccl_id, 128);
+        else NC(g_nccl.GetUniqueId(&id));
+    }
+
+    h->shards.resize(n_local);
+    for (int i = 0; i < n_local; ++i) {
+        Shard& s = h->shards[i];
+        s.dev = cfg.device_ids ? cfg.device_ids[i] : i;
+        s.world_rank = h->proc_rank * n_local + i;
+        s.row_begin = rb[i];
+        s.n_rows = rb[i + 1] - rb[i];
+        s.nnz_begin = ip[rb[i]];
+        s.nnz = ip[rb[i + 1]] - ip[rb[i]];
+        if (s.n_rows >= (1LL << 31)) return fail(TSC_ERR_ARG, "more than 2^31 reads on one GPU");
+        CU(cudaSetDevice(s.dev));
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaDeviceGetAttribute(&s.n_sm, cudaDevAttrMultiProcessorCount, s.dev));
+    }
+    if (h->world > 1) {
+        NC(g_nccl.GroupStart());
+        for (auto& s : h->shards) {
+            CU(cudaSetDevice(s.dev));
+            NC(g_nccl.CommInitRank(&s.comm, h->world, id, s.world_rank));
+        }
+        NC(g_nccl.GroupEnd());
+    }
+
+    // ---- tuning
+    h->R = cfg.replicas > 0 ? std::min(cfg.replicas, 64) : 16;
+    const double avg = n_rows ? (double)nnz / (double)n_rows : 1.0;
+    h->G = avg <= 5.0 ? 4 : avg <= 24.0 ? 8 : avg <= 64.0 ? 16 : 32;
+    h->kernel = (cfg.kernel == TSC_KERNEL_ROWS) ? TSC_KERNEL_ROWS : TSC_KERNEL_TILES;
+
+    // ---- upload + build per shard
+    std::vector<uint16_t*> raw_d(n_local, nullptr);
+    std::vector<int*> colin_d(n_local, nullptr);
+    std::vector<unsigned long long*> cnt_d(n_local, nullptr);
+    std::vector<double*> lut_d(n_local, nullptr);
+    auto cleanup_tmp = [&]() {
+        for (int i = 0; i < n_local; ++i) {
+            cudaSetDevice(h->shards[i].dev);
+            if (raw_d[i]) cudaFree(raw_d[i]);
+            if (colin_d[i]) cudaFree(colin_d[i]);
+            if (cnt_d[i]) cudaFree(cnt_d[i]);
+            if (lut_d[i]) cudaFree(lut_d[i]);
+            raw_d[i] = nullptr; colin_d[i] = nullptr; cnt_d[i] = nullptr; lut_d[i] = nullptr;
+        }
+    };
+    struct TmpGuard { std::function<void()> f; ~TmpGuard() { f(); } };
+    TmpGuard guard{cleanup_tmp};
+
+    const size_t pad = 256;
+    for (int i = 0; i < n_local; ++i) {
+        Shard& s = h->shards[i];
+        CU(cudaSetDevice(s.dev));
+        CU(cudaMalloc(&s.indptr, sizeof(long long) * (s.n_rows + 1)));
+        CU(cudaMalloc(&s.col, sizeof(int) * (s.nnz + pad)));
+        CU(cudaMalloc(&s.q, sizeof(double) * (s.nnz + pad)));
+        CU(cudaMalloc(&s.wy, sizeof(double) * std::max<long long>(s.n_rows, 1)));
+        CU(cudaMalloc(&raw_d[i], sizeof(uint16_t) * std::max<long long>(s.nnz, 1)));
+        CU(cudaMalloc(&colin_d[i], sizeof(int) * std::max<long long>(s.nnz, 1)));
+        CU(cudaMalloc(&cnt_d[i], sizeof(unsigned long long) * K));
+        CU(cudaMalloc(&lut_d[i], sizeof(double) * lut_len));
+        CU(cudaMalloc(&s.bad, sizeof(int)));
+        CU(cudaMemsetAsync(s.bad, 0, sizeof(int), s.stream));
+        CU(cudaMemsetAsync(cnt_d[i], 0, sizeof(unsigned long long) * K, s.stream));
+        CU(cudaMemsetAsync(s.col + s.nnz, 0, sizeof(int) * pad, s.stream));
+        CU(cudaMemsetAsync(s.q + s.nnz, 0, sizeof(double) * pad, s.stream));
+        // local read pointers rebased to the shard
+        std::vector<long long> lip((size_t)s.n_rows + 1);
+        for (long long r = 0; r <= s.n_rows; ++r) lip[r] = ip[s.row_begin + r] - s.nnz_begin;
+        CU(cudaMemcpyAsync(s.indptr, lip.data(), sizeof(long long) * (s.n_rows + 1), cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(raw_d[i], raw + s.nnz_begin, sizeof(uint16_t) * s.nnz, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(colin_d[i], indices + s.nnz_begin, sizeof(int) * s.nnz, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(lut_d[i], q_lut, sizeof(double) * lut_len, cudaMemcpyHostToDevice, s.stream));
+        h->h2d += sizeof(long long) * (s.n_rows + 1) + (sizeof(uint16_t) + sizeof(int)) * s.nnz + sizeof(double) * lut_len;
+        CU(cudaStreamSynchronize(s.stream));   // lip goes out of scope
+        k_col_hist<<<grid_for(s.nnz, 256, s.n_sm * 16), 256, 0, s.stream>>>(colin_d[i], s.nnz, K, cnt_d[i], s.bad);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+        // tiles for the fused kernel
+        std::vector<Tile> tiles;
+        build_tiles(lip.data(), s.n_rows, tiles, s.n_long);
+        s.n_tiles = (long long)tiles.size();
+        CU(cudaMalloc(&s.tiles, sizeof(Tile) * std::max<size_t>(tiles.size(), 1)));
+        CU(cudaMemcpyAsync(s.tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice, s.stream));
+        h->h2d += sizeof(Tile) * tiles.size();
+        CU(cudaStreamSynchronize(s.stream));
+    }
+    {   // global per-locus entry counts -> internal numbering (descending count, ties by original index)
+        static_assert(sizeof(unsigned long long) == 8, "");
+        if (h->world > 1) {
+            NC(g_nccl.GroupStart());
+            for (int i = 0; i < n_local; ++i) {
+                CU(cudaSetDevice(h->shards[i].dev));
+                NC(g_nccl.AllReduce(cnt_d[i], cnt_d[i], K, ncclUint64, ncclSum, h->shards[i].comm, h->shards[i].stream));
+            }
+            NC(g_nccl.GroupEnd());
+        }
+        for (auto& s : h->shards) {
+            int bad = 0;
+            CU(cudaSetDevice(s.dev));
+            CU(cudaMemcpyAsync(&bad, s.bad, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+            if (bad) return fail(TSC_ERR_ARG, "column index out of range [0, n_cols)");
+        }
+        std::vector<unsigned long long> cnt(K);
+        Shard& s0 = h->shards[0];
+        CU(cudaSetDevice(s0.dev));
+        CU(cudaMemcpyAsync(cnt.data(), cnt_d[0], sizeof(unsigned long long) * K, cudaMemcpyDeviceToHost, s0.stream));
+        CU(cudaStreamSynchronize(s0.stream));
+        h->d2h += sizeof(unsigned long long) * K;
+        h->inv.resize(K);
+        std::iota(h->inv.begin(), h->inv.end(), 0);
+        if (cfg.permute_columns)
+            std::stable_sort(h->inv.begin(), h->inv.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+        h->perm.resize(K);
+        for (int i = 0; i < K; ++i) h->perm[h->inv[i]] = i;
+    }
+    const size_t kb = sizeof(double) * K;
+    for (int i = 0; i < n_local; ++i) {
+        Shard& s = h->shards[i];
+        CU(cudaSetDevice(s.dev));
+        CU(cudaMalloc(&s.perm, sizeof(int) * K));
+        CU(cudaMemcpyAsync(s.perm, h->perm.data(), sizeof(int) * K, cudaMemcpyHostToDevice, s.stream));
+        k_build_q<<<grid_for(s.nnz, 256, s.n_sm * 16), 256, 0, s.stream>>>(raw_d[i], colin_d[i], lut_d[i], lut_len, s.perm,
+                                                                        s.q, s.col, s.nnz, s.bad);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+        double** kv[] = {&s.pi, &s.theta, &s.pt, &s.pi_prev, &s.theta_prev, &s.pt_prev, &s.pi_init, &s.theta_init,
+                         &s.pisum0, &s.thetasum, &s.ones, &s.tmp_a, &s.tmp_b, &s.tmp_c, &s.colsum};
+        for (double** p : kv) { CU(cudaMalloc(p, kb)); CU(cudaMemsetAsync(*p, 0, kb, s.stream)); }
+        CU(cudaMalloc(&s.acc, kb * h->R));
+        CU(cudaMemsetAsync(s.acc, 0, kb * h->R, s.stream));
+        CU(cudaMalloc(&s.consts, sizeof(Consts)));
+        CU(cudaMalloc(&s.st, sizeof(EmState)));
+        CU(cudaMemsetAsync(s.st, 0, sizeof(EmState), s.stream));
+        CU(cudaMallocHost(&s.st_host, sizeof(EmState) * 2));
+        CU(cudaMalloc(&s.scalars, sizeof(double) * 8));
+        CU(cudaMemsetAsync(s.scalars, 0, sizeof(double) * 8, s.stream));
+        CU(cudaEventCreateWithFlags(&s.ev_poll[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_poll[1], cudaEventDisableTiming));
+        s.grid_rows = s.n_sm * 4;                   // 512-thread blocks, persistent grid-stride
+        s.grid_tiles = s.n_sm * 2;
+        CU(cudaMalloc(&s.partials, sizeof(double) * s.grid_rows));
+        k_row_init<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(csr_of(s), s.wy, s.scalars, s.pisum0);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+        k_fill<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.ones, K, 1.0);
+        LAUNCH(h);
+        k_fill<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.pi, K, 1.0 / K);        // model.py:667
+        LAUNCH(h);
+        k_fill<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.theta, K, 1.0 / K);     // model.py:673
+        LAUNCH(h);
+        k_mul<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.pi, s.theta, s.pt, K);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+    }
+    // totals over all shards (model.py:691-699)
+    ALLREDUCE(h, s.scalars, 2, ncclFloat64, ncclSum);
+    ALLREDUCE(h, s.scalars + 2, 1, ncclFloat64, ncclMax);
+    ALLREDUCE(h, s.pisum0, (size_t)K, ncclFloat64, ncclSum);
+    for (auto& s : h->shards) {
+        int bad = 0;
+        double part[3];
+        CU(cudaSetDevice(s.dev));
+        CU(cudaMemcpyAsync(&bad, s.bad, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(part, s.scalars, sizeof(double) * 3, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        if (bad) return fail(TSC_ERR_ARG, "raw score >= lut_len");
+        Consts c;
+        c.total_wt = part[0];
+        c.ambig_wt = part[1];
+        c.wmax = part[2];
+        c.pi_prior_wt = pi_prior * c.wmax;                           // model.py:696
+        c.theta_prior_wt = theta_prior * c.wmax;                     // model.py:697
+        c.theta_denom = c.ambig_wt + c.theta_prior_wt * K;           // model.py:734
+        c.pi_denom = c.total_wt + c.pi_prior_wt * K;                 // model.py:739
+        h->consts = c;
+        CU(cudaMemcpyAsync(s.consts, &c, sizeof(Consts), cudaMemcpyHostToDevice, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+    }
+    // shared-memory staging of the pi*theta table (optional)
+    {
+        int want = cfg.smem_table_cols;
+        if (want < 0) want = 0;                       // auto: gather through L1/L2 (measured faster when loci are skewed)
+        want = std::min(want, K);
+        for (auto& s : h->shards) {
+            CU(cudaSetDevice(s.dev));
+            int max_optin = 0;
+            CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s.dev));
+            const size_t scratch = sizeof(double) * kTileWarps * kScratch;
+            const int fit = (int)((max_optin - scratch - 1024) / sizeof(double));
+            s.s_cols = std::min(want, std::max(fit, 0));
+            s.smem_tiles = scratch + sizeof(double) * s.s_cols;
+            CU(cudaFuncSetAttribute(k_fused_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(s.smem_tiles, scratch)));
+            CU(cudaFuncSetAttribute(k_fused_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+            if (s.s_cols > 0) { h->smem_tab = true; s.grid_tiles = s.n_sm; }
+        }
+    }
+    return sync_all(h);
+}
+
+extern "C" int tsc_create(tsc_handle** out, const tsc_config* cfg_in, int64_t n_rows, int32_t n_cols, int64_t nnz,
+                          const void* indptr, int32_t indptr_bytes, const int32_t* indices, const uint16_t* raw,
+                          const double* q_lut, int32_t lut_len, double pi_prior, double theta_prior) {
+    if (!out) return fail(TSC_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n_rows < 0 || n_cols <= 0 || nnz < 0) return fail(TSC_ERR_ARG, "negative or empty dimensions");
+    if (!indptr || (nnz > 0 && (!indices || !raw))) return fail(TSC_ERR_ARG, "NULL CSR array");
+    if (indptr_bytes != 4 && indptr_bytes != 8) return fail(TSC_ERR_ARG, "indptr_bytes must be 4 or 8");
+    if (!q_lut || lut_len <= 0) return fail(TSC_ERR_ARG, "q_lut missing");
+    tsc_config cfg;
+    if (cfg_in) cfg = *cfg_in; else tsc_config_default(&cfg);
+    tsc_handle* h = new (std::nothrow) tsc_handle();
+    if (!h) return fail(TSC_ERR_ALLOC, "out of host memory");
+    int rc = create_impl(h, cfg, n_rows, n_cols, nnz, indptr, indptr_bytes, indices, raw, q_lut, lut_len, pi_prior, theta_prior);
+    if (rc) { std::string keep = g_err; tsc_destroy(h); g_err = keep; return rc; }
+    *out = h;
+    return TSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- getters
+extern "C" int tsc_get_constants(tsc_handle* h, double* scalars5, double* pisum0) {
+    if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
+    if (scalars5) {
+        scalars5[0] = h->consts.total_wt; scalars5[1] = h->consts.ambig_wt; scalars5[2] = h->consts.wmax;
+        scalars5[3] = h->consts.pi_prior_wt; scalars5[4] = h->consts.theta_prior_wt;
+    }
+    if (pisum0) { Shard& s = h->shards[0]; CU(cudaSetDevice(s.dev)); return get_kvec(h, s, s.pisum0, pisum0); }
+    return TSC_OK;
+}
+
+extern "C" int tsc_get_row_info(tsc_handle* h, uint8_t* y_rows, double* w_rows) {
+    if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
+    std::vector<uint8_t> y;
+    std::vector<double> w;
+    const bool compact = !h->rowmap.empty() || h->n_rows != h->n_rows_user;
+    if (compact) { if (y_rows) y.resize(h->n_rows); if (w_rows) w.resize(h->n_rows); }
+    uint8_t* yh = compact ? y.data() : y_rows;
+    double* wh = compact ? w.data() : w_rows;
+    for (auto& s : h->shards) {
+        CU(cudaSetDevice(s.dev));
+        uint8_t* yd = nullptr; double* wd = nullptr;
+        if (y_rows) CU(cudaMalloc(&yd, std::max<long long>(s.n_rows, 1)));
+        if (w_rows) CU(cudaMalloc(&wd, sizeof(double) * std::max<long long>(s.n_rows, 1)));
+        k_row_info<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(csr_of(s), s.wy, yd, wd);
+        LAUNCH(h);
+        if (y_rows) CU(cudaMemcpyAsync(yh + s.row_begin, yd, s.n_rows, cudaMemcpyDeviceToHost, s.stream));
+        if (w_rows) CU(cudaMemcpyAsync(wh + s.row_begin, wd, sizeof(double) * s.n_rows, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        if (yd) cudaFree(yd);
+        if (wd) cudaFree(wd);
+        h->d2h += (y_rows ? s.n_rows : 0) + (w_rows ? 8 * s.n_rows : 0);
+    }
+    if (compact) {
+        if (y_rows) { memset(y_rows, 0, h->n_rows_user); for (long long r = 0; r < h->n_rows; ++r) y_rows[h->rowmap[r]] = y[r]; }
+        if (w_rows) { std::fill(w_rows, w_rows + h->n_rows_user, 0.0); for (long long r = 0; r < h->n_rows; ++r) w_rows[h->rowmap[r]] = w[r]; }
+    }
+    return TSC_OK;
+}
+
+extern "C" int tsc_get_q(tsc_handle* h, double* q_data) {
+    if (!h || !q_data) return fail(TSC_ERR_ARG, "NULL argument");
+    for (auto& s : h->shards) {
+        CU(cudaSetDevice(s.dev));
+        CU(cudaMemcpyAsync(q_data + s.nnz_begin, s.q, sizeof(double) * s.nnz, cudaMemcpyDeviceToHost, s.stream));
+        h->d2h += sizeof(double) * s.nnz;
+    }
+    return sync_all(h);
+}
+
+extern "C" int tsc_get_params(tsc_handle* h, double* pi, double* theta, double* pi_init, double* theta_init) {
+    if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
+    Shard& s = h->shards[0];
+    CU(cudaSetDevice(s.dev));
+    int rc;
+    if (pi && (rc = get_kvec(h, s, s.pi, pi))) return rc;
+    if (theta && (rc = get_kvec(h, s, s.theta, theta))) return rc;
+    if ((pi_init || theta_init) && h->n_iter == 0) return fail(TSC_ERR_STATE, "pi_init/theta_init exist only after em()");
+    if (pi_init && (rc = get_kvec(h, s, s.pi_init, pi_init))) return rc;
+    if (theta_init && (rc = get_kvec(h, s, s.theta_init, theta_init))) return rc;
+    return TSC_OK;
+}
+
+extern "C" int tsc_set_params(tsc_handle* h, const double* pi, const double* theta) {
+    if (!h || !pi || !theta) return fail(TSC_ERR_ARG, "NULL argument");
+    for (auto& s : h->shards) {
+        CU(cudaSetDevice(s.dev));
+        int rc;
+        if ((rc = put_kvec(h, s, pi, s.pi))) return rc;
+        if ((rc = put_kvec(h, s, theta, s.theta))) return rc;
+        k_mul<<<grid_for(h->K, 256, 1 << 20), 256, 0, s.stream>>>(s.pi, s.theta, s.pt, h->K);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+    }
+    return sync_all(h);
+}
+
+extern "C" int tsc_get_counters(tsc_handle* h, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
+    if (launches) *launches = h->launches;
+    if (h2d_bytes) *h2d_bytes = h->h2d;
+    if (d2h_bytes) *d2h_bytes = h->d2h;
+    return TSC_OK;
+}
+
+extern "C" int tsc_get_kernel_times(tsc_handle* h, float* ms_out, int32_t max_n, int32_t* n_out) {
+    if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
+    const int n = (int)std::min<size_t>(h->kernel_ms.size(), (size_t)std::max(max_n, 0));
+    if (ms_out) for (int i = 0; i < n; ++i) ms_out[i] = h->kernel_ms[i];
+    if (n_out) *n_out = (int)h->kernel_ms.size();
+    return TSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- EM
+static int launch_fused(tsc_handle* h, Shard& s) {
+    if (h->kernel == TSC_KERNEL_ROWS) {
+        launch_rows(h->G, [&](auto g) {
+            k_fused_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), s.wy, s.pt, s.acc, h->K, h->R, s.st);
+        });
+    } else if (s.s_cols > 0) {
+        k_fused_tiles<true><<<s.grid_tiles, kTileThreads, s.smem_tiles, s.stream>>>(s.tiles, s.n_tiles, s.q, s.col, s.wy, s.pt,
+                                                                                   s.acc, h->K, h->R, s.s_cols, s.st);
+    } else {
+        k_fused_tiles<false><<<s.grid_tiles, kTileThreads, sizeof(double) * kTileWarps * kScratch, s.stream>>>(
+            s.tiles, s.n_tiles, s.q, s.col, s.wy, s.pt, s.acc, h->K, h->R, 0, s.st);
+    }
+    LAUNCH(h);
+    CU(cudaGetLastError());
+    return TSC_OK;
+}
+
+// global log-likelihood into s.scalars[4] of every shard (model.py:744-760)
+static int launch_lnl(tsc_handle* h, const double* (*zin_of)(Shard&), bool from_prev, bool gated,
+                      const double* (*ia)(Shard&), const double* (*iu)(Shard&)) {
+    for (auto& s : h->shards) {
+        CU(cudaSetDevice(s.dev));
+        const double* zin = zin_of ? zin_of(s) : nullptr;
+        const EmState* st = gated ? s.st : nullptr;
+        launch_rows(h->G, [&](auto g) {
+            k_lnl_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(
+                csr_of(s), zin, from_prev ? s.pt_prev : nullptr, from_prev ? s.pi_prev : nullptr, ia(s), iu(s), s.partials, st);
+        });
+        LAUNCH(h);
+        CU(cudaGetLastError());
+        if (!gated) {
+            k_sum_partials<<<1, 1024, 0, s.stream>>>(s.partials, s.grid_rows, s.scalars + 4);
+            LAUNCH(h);
+        } else {
+            // when the loop is already done the partials are stale; k_lnl_control ignores the value
+            k_sum_partials<<<1, 1024, 0, s.stream>>>(s.partials, s.grid_rows, s.scalars + 4);
+            LAUNCH(h);
+        }
+        CU(cudaGetLastError());
+    }
+    ALLREDUCE(h, s.scalars + 4, 1, ncclFloat64, ncclSum);
+    return TSC_OK;
+}
+
+extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_likelihood, double* diffs_out,
+                      double* lnls_out, int32_t* n_iter, int32_t* converged, double* final_lnl) {
+    if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
+    if (use_likelihood && !lnls_out) return fail(TSC_ERR_ARG, "lnls_out required with use_likelihood");
+    const int T = std::max(1, (int)max_iter);   // the reference's loop body always runs once (model.py:771-794)
+    const int K = h->K;
+    const double inf = std::numeric_limits<double>::infinity();
+    for (auto& s : h->shards) {
+        CU(cudaSetDevice(s.dev));
+        if (s.diffs_cap < T) {
+            if (s.diffs) cudaFree(s.diffs);
+            if (s.lnls) cudaFree(s.lnls);
+            CU(cudaMalloc(&s.diffs, sizeof(double) * T));
+            CU(cudaMalloc(&s.lnls, sizeof(double) * T));
+            s.diffs_cap = T;
+        }
+        EmState st0{};
+        st0.lnl_prev = h->lnl;          // self.lnl carries over between em() calls (model.py:683,786)
+        st0.lnl = h->lnl;
+        s.st_host[0] = st0;
+        s.st_host[1] = st0;
+        CU(cudaMemcpyAsync(s.st, &s.st_host[0], sizeof(EmState), cudaMemcpyHostToDevice, s.stream));
+    }
+    Shard& s0 = h->shards[0];
+    CU(cudaSetDevice(s0.dev));
+    while ((int)s0.ev_k.size() < 2 * T) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        s0.ev_k.push_back(e);
+    }
+    const int poll_every = 4;
+    int issued = 0, polls = 0;
+    bool stop = false;
+    for (int it = 0; it < T && !stop; ++it) {
+        for (auto& s : h->shards) {
+            CU(cudaSetDevice(s.dev));
+            if (&s == &s0) CU(cudaEventRecord(s0.ev_k[2 * it], s.stream));
+            int rc = launch_fused(h, s);
+            if (rc) return rc;
+            if (&s == &s0) CU(cudaEventRecord(s0.ev_k[2 * it + 1], s.stream));
+            k_reduce_replicas<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.acc, K, h->R, s.thetasum, s.st);
+            LAUNCH(h);
+            CU(cudaGetLastError());
+        }
+        ALLREDUCE(h, s.thetasum, (size_t)K, ncclFloat64, ncclSum);
+        for (auto& s : h->shards) {
+            CU(cudaSetDevice(s.dev));
+            UpdateArgs a{s.thetasum, s.pisum0, s.consts, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
+                         s.pi_init, s.theta_init, s.st, s.diffs, K, T, use_likelihood ? 1 : 0, eps};
+            k_update<<<1, 1024, 0, s.stream>>>(a);
+            LAUNCH(h);
+            CU(cudaGetLastError());
+        }
+        if (use_likelihood) {
+            int rc = launch_lnl(h, nullptr, true, true,
+                                [](Shard& s) -> const double* { return s.pt; }, [](Shard& s) -> const double* { return s.pi; });
+            if (rc) return rc;
+            for (auto& s : h->shards) {
+                CU(cudaSetDevice(s.dev));
+                k_lnl_control<<<1, 1, 0, s.stream>>>(s.st, s.scalars + 4, s.lnls, eps, T);
+                LAUNCH(h);
+                CU(cudaGetLastError());
+            }
+        }
+        ++issued;
+        if (issued % poll_every == 0 || it == T - 1) {
+            CU(cudaSetDevice(s0.dev));
+            const int slot = polls & 1;
+            CU(cudaMemcpyAsync(&s0.st_host[slot], s0.st, sizeof(EmState), cudaMemcpyDeviceToHost, s0.stream));
+            CU(cudaEventRecord(s0.ev_poll[slot], s0.stream));
+            if (polls > 0) {
+                CU(cudaEventSynchronize(s0.ev_poll[slot ^ 1]));
+                if (s0.st_host[slot ^ 1].done) stop = true;
+            }
+            ++polls;
+        }
+    }
+    int rc = sync_all(h);
+    if (rc) return rc;
+    EmState fin;
+    CU(cudaSetDevice(s0.dev));
+    CU(cudaMemcpy(&fin, s0.st, sizeof(EmState), cudaMemcpyDeviceToHost));
+    h->n_iter = fin.iter;
+    h->converged = fin.converged;
+    h->em_done = true;
+    h->kernel_ms.clear();
+    for (int it = 0; it < std::min(issued, fin.iter); ++it) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s0.ev_k[2 * it], s0.ev_k[2 * it + 1]));
+        h->kernel_ms.push_back(ms);
+    }
+    if (use_likelihood) {
+        h->lnl = fin.lnl;
+    } else {   // model.py:800-801
+        rc = launch_lnl(h, nullptr, true, false,
+                        [](Shard& s) -> const double* { return s.pt; }, [](Shard& s) -> const double* { return s.pi; });
+        if (rc) return rc;
+        CU(cudaSetDevice(s0.dev));
+        CU(cudaMemcpyAsync(&h->lnl, s0.scalars + 4, sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+        CU(cudaStreamSynchronize(s0.stream));
+        rc = sync_all(h);
+        if (rc) return rc;
+    }
+    if (diffs_out) CU(cudaMemcpy(diffs_out, s0.diffs, sizeof(double) * fin.iter, cudaMemcpyDeviceToHost));
+    if (lnls_out && use_likelihood) CU(cudaMemcpy(lnls_out, s0.lnls, sizeof(double) * fin.iter, cudaMemcpyDeviceToHost));
+    h->d2h += sizeof(double) * fin.iter * (use_likelihood ? 2 : 1) + sizeof(EmState);
+    if (n_iter) *n_iter = fin.iter;
+    if (converged) *converged = fin.converged;
+    if (final_lnl) *final_lnl = h->lnl;
+    (void)inf;
+    return TSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- estep / mstep / lnl
+static int alloc_entries(Shard& s, double** p) {
+    CU(cudaSetDevice(s.dev));
+    CU(cudaMalloc(p, sizeof(double) * std::max<long long>(s.nnz, 1)));
+    return TSC_OK;
+}
+
+static int z_to_host(tsc_handle* h, const double* tab_amb_sel, int which, double* z_data) {
+    // which: 0 = tables tmp_c/tmp_a (explicit pi, theta), 1 = *_prev (stored posterior), 2 = ones (Q.norm(1))
+    (void)tab_amb_sel;
+    for (auto& s : h->shards) {
+        double* zd = nullptr;
+        int rc = alloc_entries(s, &zd);
+        if (rc) return rc;
+        const double* ta = which == 0 ? s.tmp_c : which == 1 ? s.pt_prev : s.ones;
+        const double* tu = which == 0 ? s.tmp_a : which == 1 ? s.pi_prev : s.ones;
+        launch_rows(h->G, [&](auto g) {
+            k_estep_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, zd);
+        });
+        LAUNCH(h);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(z_data + s.nnz_begin, zd, sizeof(double) * s.nnz, cudaMemcpyDeviceToHost, s.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+        cudaFree(zd);
+        if (e != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("posterior export: ") + cudaGetErrorString(e));
+        h->d2h += sizeof(double) * s.nnz;
+    }
+    return TSC_OK;
+}
+
+static int upload_pi_theta(tsc_handle* h, const double* pi, const double* theta) {
+    for (auto& s : h->shards) {
+        CU(cudaSetDevice(s.dev));
+        int rc;
+        if ((rc = put_kvec(h, s, pi, s.tmp_a))) return rc;
+        if ((rc = put_kvec(h, s, theta, s.tmp_b))) return rc;
+        k_mul<<<grid_for(h->K, 256, 1 << 20), 256, 0, s.stream>>>(s.tmp_a, s.tmp_b, s.tmp_c, h->K);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+    }
+    return TSC_OK;
+}
+
+extern "C" int tsc_estep(tsc_handle* h, const double* pi, const double* theta, double* z_data) {
+    if (!h || !pi || !theta || !z_data) return fail(TSC_ERR_ARG, "NULL argument");
+    int rc = upload_pi_theta(h, pi, theta);
+    if (rc) return rc;
+    return z_to_host(h, nullptr, 0, z_data);
+}
+
+extern "C" int tsc_get_z(tsc_handle* h, int32_t initial, double* z_data) {
+    if (!h || !z_data) return fail(TSC_ERR_ARG, "NULL argument");
+    if (!initial && !h->em_done) return fail(TSC_ERR_STATE, "z exists only after em() (model.py:659,795)");
+    return z_to_host(h, nullptr, initial ? 2 : 1, z_data);
+}
+
+__global__ void k_mstep_tail(const double* __restrict__ thetasum, const double* __restrict__ pisum0, const Consts* __restrict__ c,
+                             double* __restrict__ pi_hat, double* __restrict__ theta_hat, int K) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    const double ts = thetasum[j];
+    theta_hat[j] = (ts + c->theta_prior_wt) / c->theta_denom;
+    const double pisum = pisum0[j] + ts;
+    pi_hat[j] = (pisum + c->pi_prior_wt) / c->pi_denom;
+}
+
+extern "C" int tsc_mstep(tsc_handle* h, const double* z_data, double* pi_hat, double* theta_hat) {
+    if (!h || !z_data || !pi_hat || !theta_hat) return fail(TSC_ERR_ARG, "NULL argument");
+    const int K = h->K;
+    for (auto& s : h->shards) {
+        double* zd = nullptr;
+        int rc = alloc_entries(s, &zd);
+        if (rc) return rc;
+        cudaError_t e = cudaMemcpyAsync(zd, z_data + s.nnz_begin, sizeof(double) * s.nnz, cudaMemcpyHostToDevice, s.stream);
+        h->h2d += sizeof(double) * s.nnz;
+        if (e == cudaSuccess) {
+            launch_rows(h->G, [&](auto g) {
+                k_mstep_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), s.wy, zd, s.acc, K, h->R);
+            });
+            LAUNCH(h);
+            k_reduce_replicas<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.acc, K, h->R, s.tmp_c, nullptr);
+            LAUNCH(h);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+        cudaFree(zd);
+        if (e != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("mstep: ") + cudaGetErrorString(e));
+    }
+    ALLREDUCE(h, s.tmp_c, (size_t)K, ncclFloat64, ncclSum);
+    Shard& s = h->shards[0];
+    CU(cudaSetDevice(s.dev));
+    k_mstep_tail<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.tmp_c, s.pisum0, s.consts, s.tmp_a, s.tmp_b, K);
+    LAUNCH(h);
+    CU(cudaGetLastError());
+    int rc = sync_all(h);
+    if (rc) return rc;
+    if ((rc = get_kvec(h, s, s.tmp_a, pi_hat))) return rc;
+    return get_kvec(h, s, s.tmp_b, theta_hat);
+}
+
+extern "C" int tsc_calculate_lnl(tsc_handle* h, const double* z_data, const double* pi, const double* theta, double* lnl) {
+    if (!h || !z_data || !pi || !theta || !lnl) return fail(TSC_ERR_ARG, "NULL argument");
+    int rc = upload_pi_theta(h, pi, theta);
+    if (rc) return rc;
+    std::vector<double*> zd(h->shards.size(), nullptr);
+    auto free_all = [&]() { for (size_t i = 0; i < zd.size(); ++i) if (zd[i]) { cudaSetDevice(h->shards[i].dev); cudaFree(zd[i]); } };
+    for (size_t i = 0; i < h->shards.size(); ++i) {
+        Shard& s = h->shards[i];
+        if ((rc = alloc_entries(s, &zd[i]))) { free_all(); return rc; }
+        cudaError_t e = cudaMemcpyAsync(zd[i], z_data + s.nnz_begin, sizeof(double) * s.nnz, cudaMemcpyHostToDevice, s.stream);
+        h->h2d += sizeof(double) * s.nnz;
+        if (e == cudaSuccess) {
+            launch_rows(h->G, [&](auto g) {
+                k_lnl_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), zd[i], nullptr, nullptr, s.tmp_c, s.tmp_a,
+                                                                                s.partials, nullptr);
+            });
+            LAUNCH(h);
+            k_sum_partials<<<1, 1024, 0, s.stream>>>(s.partials, s.grid_rows, s.scalars + 4);
+            LAUNCH(h);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) { free_all(); return fail(TSC_ERR_CUDA, std::string("calculate_lnl: ") + cudaGetErrorString(e)); }
+    }
+    rc = allreduce(h, 0, [](Shard& s) -> void* { return (void*)(s.scalars + 4); }, 1, ncclFloat64, ncclSum);
+    if (!rc) rc = sync_all(h);
+    free_all();
+    if (rc) return rc;
+    Shard& s = h->shards[0];
+    CU(cudaSetDevice(s.dev));
+    CU(cudaMemcpy(lnl, s.scalars + 4, sizeof(double), cudaMemcpyDeviceToHost));
+    return TSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- reassign
+static int reassign_impl(tsc_handle* h, int method, double thresh, int initial, const int32_t* picks,
+                         int32_t* nbest_rows, double* colsum, double* data) {
+    if (method < 0 || method > 5) return fail(TSC_ERR_ARG, "Argument \"method\" should be one of (exclude, choose, average, conf, unique, all)");
+    if (!initial && !h->em_done) return fail(TSC_ERR_STATE, "reassign(initial=False) needs em() first (self.z is None, model.py:659)");
+    const int K = h->K;
+    const bool compact = !h->rowmap.empty();
+    std::vector<int32_t> picks_c, nbest_c;
+    if (compact && picks) { picks_c.resize(h->n_rows); for (long long r = 0; r < h->n_rows; ++r) picks_c[r] = picks[h->rowmap[r]]; }
+    if (compact && nbest_rows) nbest_c.resize(h->n_rows);
+    const int32_t* picks_h = compact ? (picks ? picks_c.data() : nullptr) : picks;
+    int32_t* nbest_h = compact ? (nbest_rows ? nbest_c.data() : nullptr) : nbest_rows;
+    for (auto& s : h->shards) {
+        CU(cudaSetDevice(s.dev));
+        int *picks_d = nullptr, *nbest_d = nullptr;
+        double* data_d = nullptr;
+        cudaError_t e = cudaSuccess;
+        const size_t rb = sizeof(int) * std::max<long long>(s.n_rows, 1);
+        if (picks_h && method == TSC_CHOOSE) {
+            e = cudaMalloc(&picks_d, rb);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(picks_d, picks_h + s.row_begin, sizeof(int) * s.n_rows, cudaMemcpyHostToDevice, s.stream);
+            h->h2d += sizeof(int) * s.n_rows;
+        }
+        if (e == cudaSuccess && nbest_h) e = cudaMalloc(&nbest_d, rb);
+        if (e == cudaSuccess && data) e = cudaMalloc(&data_d, sizeof(double) * std::max<long long>(s.nnz, 1));
+        if (e == cudaSuccess && colsum) e = cudaMemsetAsync(s.colsum, 0, sizeof(double) * K, s.stream);
+        if (e == cudaSuccess) {
+            ReassignArgs g{method, thresh, picks_d, nbest_d, colsum ? s.colsum : nullptr, data_d};
+            const double* ta = initial ? s.ones : s.pt_prev;
+            const double* tu = initial ? s.ones : s.pi_prev;
+            launch_rows(h->G, [&](auto gg) {
+                k_reassign_rows<decltype(gg)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, g);
+            });
+            LAUNCH(h);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && nbest_h) { e = cudaMemcpyAsync(nbest_h + s.row_begin, nbest_d, sizeof(int) * s.n_rows, cudaMemcpyDeviceToHost, s.stream); h->d2h += sizeof(int) * s.n_rows; }
+        if (e == cudaSuccess && data) { e = cudaMemcpyAsync(data + s.nnz_begin, data_d, sizeof(double) * s.nnz, cudaMemcpyDeviceToHost, s.stream); h->d2h += sizeof(double) * s.nnz; }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+        if (picks_d) cudaFree(picks_d);
+        if (nbest_d) cudaFree(nbest_d);
+        if (data_d) cudaFree(data_d);
+        if (e != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("reassign: ") + cudaGetErrorString(e));
+    }
+    if (compact && nbest_rows) {
+        std::fill(nbest_rows, nbest_rows + h->n_rows_user, 0);
+        for (long long r = 0; r < h->n_rows; ++r) nbest_rows[h->rowmap[r]] = nbest_c[r];
+    }
+    if (colsum) {
+        ALLREDUCE(h, s.colsum, (size_t)K, ncclFloat64, ncclSum);
+        int rc = sync_all(h);
+        if (rc) return rc;
+        Shard& s = h->shards[0];
+        CU(cudaSetDevice(s.dev));
+        return get_kvec(h, s, s.colsum, colsum);
+    }
+    return TSC_OK;
+}
+
+extern "C" int tsc_reassign_nbest(tsc_handle* h, int32_t initial, int32_t* nbest_rows) {
+    if (!h || !nbest_rows) return fail(TSC_ERR_ARG, "NULL argument");
+    return reassign_impl(h, TSC_EXCLUDE, 0.0, initial, nullptr, nbest_rows, nullptr, nullptr);
+}
+extern "C" int tsc_reassign_colsum(tsc_handle* h, int32_t method, double thresh, int32_t initial, const int32_t* picks, double* colsum) {
+    if (!h || !colsum) return fail(TSC_ERR_ARG, "NULL argument");
+    return reassign_impl(h, method, thresh, initial, picks, nullptr, colsum, nullptr);
+}
+extern "C" int tsc_reassign_data(tsc_handle* h, int32_t method, double thresh, int32_t initial, const int32_t* picks, double* data) {
+    if (!h || !data) return fail(TSC_ERR_ARG, "NULL argument");
+    return reassign_impl(h, method, thresh, initial, picks, nullptr, nullptr, data);
+}

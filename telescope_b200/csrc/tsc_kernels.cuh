@@ -1,0 +1,469 @@
+// Device code of libtelescope_b200: Telescope's EM reassignment path on sm_100a.
+//
+// Two families of kernels work on the same HBM-resident CSR shard (fp64 Q values, int32 locus indices, int64 row
+// pointers, one shard per GPU):
+//   * "rows" kernels  -- one sub-warp of G lanes per read.  Simple; used for every one-off pass (init, posterior
+//     export, log-likelihood, the six reassign modes) and as the in-library cross-check of the fast path.
+//   * "tiles" kernel  -- the per-iteration fused E+M step (tsc_tiles.cuh): flat 128-entry tiles, 128-bit loads,
+//     warp segmented scan, scatter-add of z*w into L2-resident accumulator replicas.
+//
+// Arithmetic follows the reference's operation order wherever it changes bits (compiled with -fmad=false):
+//   n = Q * (pi*theta)  or  Q * pi          telescope/utils/model.py:718-720
+//   z = n * recip0(sum_j n)                 telescope/utils/sparse_plus.py:16-22,52
+//   c = (z * w) * Y                         telescope/utils/model.py:730-733
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tsc {
+
+struct EmState {          // lives in device memory, mirrored to pinned host memory for polling
+    int iter;             // completed iterations (model.py:775 inum)
+    int done;             // converged || reached_max -- kernels of later iterations exit immediately
+    int converged;
+    int pad;
+    double lnl_prev;      // self.lnl inside the loop when use_likelihood (model.py:786-789)
+    double lnl;
+    double diff;
+};
+
+struct Consts {           // model.py:690-697,734,739
+    double total_wt, ambig_wt, wmax, pi_prior_wt, theta_prior_wt, pi_denom, theta_denom;
+};
+
+struct Csr {              // one shard
+    const long long* indptr;   // n_rows + 1
+    const int* col;            // nnz (+ padding), internal (frequency-ordered) locus numbering
+    const double* q;           // nnz (+ padding)
+    long long n_rows;
+};
+
+__device__ __forceinline__ double recip0(double s) {
+    // sparse_plus.py:16-22: 1/v with inf -> 0.  (1/denormal overflows to inf in numpy too, and is zeroed likewise.)
+    double r = 1.0 / s;
+    return isinf(r) ? 0.0 : r;
+}
+
+template <int G>
+struct GroupBits { static constexpr unsigned value = (1u << (G & 31)) - 1u; };
+template <>
+struct GroupBits<32> { static constexpr unsigned value = 0xffffffffu; };
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+    const unsigned lane = threadIdx.x & 31u;
+    return GroupBits<G>::value << (lane & ~(unsigned)(G - 1));
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v, unsigned m) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o, G);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ double group_max(double v, unsigned m) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(m, v, o, G));
+    return v;
+}
+template <int G>
+__device__ __forceinline__ int group_sum_int(int v, unsigned m) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o, G);
+    return v;
+}
+
+// deterministic block reduction (fixed tree), result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* s_warp /* >= 32 doubles */) {
+    v = group_sum<32>(v, 0xffffffffu);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) s_warp[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? s_warp[threadIdx.x] : 0.0;
+    if (w == 0) v = group_sum<32>(v, 0xffffffffu);
+    return v;
+}
+__device__ __forceinline__ double block_max(double v, double* s_warp) {
+    v = group_max<32>(v, 0xffffffffu);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) s_warp[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? s_warp[threadIdx.x] : 0.0;
+    if (w == 0) v = group_max<32>(v, 0xffffffffu);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// construction (model.py:635-700)
+// ---------------------------------------------------------------------------------------------------------------
+
+// Q = LUT[raw] (the LUT is numpy's expm1 evaluated on the host, so Q is bit-identical to model.py:653) and locus
+// renumbering, one pass, 8 entries per thread.
+__global__ void k_build_q(const uint16_t* __restrict__ raw, const int* __restrict__ col_in,
+                          const double* __restrict__ lut, int lut_len, const int* __restrict__ perm,
+                          double* __restrict__ q, int* __restrict__ col, long long nnz, int* __restrict__ bad) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) {
+        const int s = raw[i];
+        if (s >= lut_len) { *bad = 1; q[i] = 0.0; } else q[i] = __ldg(lut + s);
+        col[i] = perm ? __ldg(perm + col_in[i]) : col_in[i];
+    }
+}
+
+__global__ void k_col_hist(const int* __restrict__ col, long long nnz, int n_cols,
+                           unsigned long long* __restrict__ cnt, int* __restrict__ bad) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) {
+        const int c = col[i];
+        if (c < 0 || c >= n_cols) { *bad = 1; continue; }
+        atomicAdd(cnt + c, 1ULL);
+    }
+}
+
+// w_i = max_j Q_ij (model.py:690); wy_i = w_i * Y_i with Y_i = [row has > 1 entries] (model.py:679);
+// partial[0] += sum w, partial[1] += sum wy, partial[2] = max w; pisum0_j += Q_ij over unique reads (model.py:699).
+__global__ void k_row_init(Csr a, double* __restrict__ wy, double* __restrict__ partial,
+                           double* __restrict__ pisum0) {
+    __shared__ double s_red[32];
+    double sw = 0, swy = 0, mw = 0;
+    long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; r < a.n_rows; r += stride) {
+        const long long s = a.indptr[r], e = a.indptr[r + 1];
+        double w = 0;                                   // sparse max: implicit zeros unless the row is full; Q >= 0
+        for (long long k = s; k < e; ++k) w = fmax(w, a.q[k]);
+        const bool amb = (e - s) > 1;
+        wy[r] = amb ? w : 0.0;
+        sw += w;
+        if (amb) swy += w;
+        mw = fmax(mw, w);
+        if (!amb && e > s) atomicAdd(pisum0 + a.col[s], a.q[s]);
+    }
+    sw = block_sum(sw, s_red);
+    if (threadIdx.x == 0) atomicAdd(partial + 0, sw);
+    swy = block_sum(swy, s_red);
+    if (threadIdx.x == 0) atomicAdd(partial + 1, swy);
+    mw = block_max(mw, s_red);
+    if (threadIdx.x == 0)   // non-negative doubles order like their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long*>(partial + 2), (unsigned long long)__double_as_longlong(mw));
+}
+
+__global__ void k_fill(double* __restrict__ p, long long n, double v) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// tab[j] = a[j] * b[j]  (pi*theta, model.py:718)
+__global__ void k_mul(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] * b[i];
+}
+
+// out[perm[j]] = in[j] (to internal numbering) or out[j] = in[perm[j]] (back)
+__global__ void k_permute(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ perm,
+                          int n, int to_internal) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) { if (to_internal) out[perm[j]] = in[j]; else out[j] = in[perm[j]]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-iteration K-length kernels
+// ---------------------------------------------------------------------------------------------------------------
+
+// thetasum_j = sum over the R accumulator replicas in fixed order; replicas are zeroed for the next iteration.
+__global__ void k_reduce_replicas(double* __restrict__ acc, int K, int R, double* __restrict__ thetasum,
+                                  const EmState* __restrict__ st) {
+    if (st && st->done) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    double s = 0;
+    for (int r = 0; r < R; ++r) { s += acc[(size_t)r * K + j]; acc[(size_t)r * K + j] = 0.0; }
+    thetasum[j] = s;
+}
+
+struct UpdateArgs {
+    const double* thetasum;   // global (all-reduced) per-locus sums of z*w*Y
+    const double* pisum0;
+    const Consts* c;
+    double *pi, *theta, *pt;                  // current parameters; overwritten with the new estimates
+    double *pi_prev, *theta_prev, *pt_prev;   // parameters the last E-step used (the stored z of model.py:795)
+    double *pi_init, *theta_init;
+    EmState* st;
+    double* diffs;
+    int K, max_iter, use_lnl;
+    double eps;
+};
+
+// mstep tail (model.py:734-742), diff_est (model.py:781) and the loop control of model.py:788-796.  One block:
+// K <= a few 10^5 and the reduction order must not depend on the launch shape.
+__global__ void __launch_bounds__(1024) k_update(UpdateArgs a) {
+    __shared__ double s_red[32];
+    EmState* st = a.st;
+    if (st->done) return;
+    const int iter = st->iter;
+    const Consts c = *a.c;
+    double local = 0;
+    for (int j = threadIdx.x; j < a.K; j += blockDim.x) {
+        const double ts = a.thetasum[j];
+        const double th = (ts + c.theta_prior_wt) / c.theta_denom;
+        const double pisum = a.pisum0[j] + ts;
+        const double pn = (pisum + c.pi_prior_wt) / c.pi_denom;
+        const double po = a.pi[j];
+        local += fabs(pn - po);
+        a.pi_prev[j] = po; a.theta_prev[j] = a.theta[j]; a.pt_prev[j] = a.pt[j];
+        a.pi[j] = pn; a.theta[j] = th; a.pt[j] = pn * th;
+        if (iter == 0) { a.pi_init[j] = pn; a.theta_init[j] = th; }
+    }
+    const double diff = block_sum(local, s_red);
+    if (threadIdx.x == 0) {
+        a.diffs[iter] = diff;
+        st->diff = diff;
+        st->iter = iter + 1;
+        if (!a.use_lnl) {
+            const int conv = diff < a.eps;
+            st->converged = conv;
+            st->done = conv || (iter + 1 >= a.max_iter);
+        }
+    }
+}
+
+// use_likelihood loop control (model.py:785-789): lnl is the all-reduced log-likelihood of this iteration
+__global__ void k_lnl_control(EmState* st, const double* lnl, double* lnls, double eps, int max_iter) {
+    if (st->done) return;
+    const double v = *lnl;
+    lnls[st->iter - 1] = v;
+    const int conv = fabs(v - st->lnl_prev) < eps;
+    st->lnl_prev = v;
+    st->lnl = v;
+    st->converged = conv;
+    st->done = conv || (st->iter >= max_iter);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// "rows" kernels: G lanes per read
+// ---------------------------------------------------------------------------------------------------------------
+
+// One read: lanes stride over its entries, n = Q * tab[col]; returns the group-wide sum.  The first chunk's values
+// stay in registers (n0, c0, k0) so that reads with <= G entries are touched once.
+template <int G>
+__device__ __forceinline__ double row_numerators(const Csr& a, long long s, long long e, const double* __restrict__ tab,
+                                                 unsigned m, int lane, double& n0, int& c0) {
+    double sum = 0;
+    n0 = 0; c0 = 0;
+    long long k = s + lane;
+    if (k < e) { c0 = a.col[k]; n0 = a.q[k] * __ldg(tab + c0); sum = n0; k += G; }
+    for (; k < e; k += G) sum += a.q[k] * __ldg(tab + a.col[k]);
+    return group_sum<G>(sum, m);
+}
+
+// Fused E-step + M-step accumulation for one EM iteration (model.py:718-722 + 730-733): nothing but the K-length
+// accumulator is written.  pt = pi*theta.  Unique reads (Y=0) contribute nothing here (they are in pisum0).
+template <int G>
+__global__ void __launch_bounds__(512) k_fused_rows(Csr a, const double* __restrict__ wy, const double* __restrict__ pt,
+                                                    double* __restrict__ acc, int K, int R, const EmState* __restrict__ st) {
+    if (st->done) return;
+    double* my = acc + (size_t)(blockIdx.x % R) * K;
+    const unsigned m = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long)gridDim.x * blockDim.x / G;
+    for (; r < a.n_rows; r += ngrp) {
+        const long long s = a.indptr[r], e = a.indptr[r + 1];
+        if (e - s < 2) continue;
+        double n0; int c0;
+        const double sum = row_numerators<G>(a, s, e, pt, m, lane, n0, c0);
+        const double rr = recip0(sum);
+        const double w = wy[r];
+        long long k = s + lane;
+        if (k < e) { const double c = (n0 * rr) * w; if (c != 0.0) atomicAdd(my + c0, c); k += G; }
+        for (; k < e; k += G) {
+            const int cc = a.col[k];
+            const double c = ((a.q[k] * __ldg(pt + cc)) * rr) * w;
+            if (c != 0.0) atomicAdd(my + cc, c);
+        }
+    }
+}
+
+// E-step alone (model.py:702-722): z for every stored entry.  tab_amb = pi*theta, tab_uni = pi.
+template <int G>
+__global__ void __launch_bounds__(512) k_estep_rows(Csr a, const double* __restrict__ tab_amb, const double* __restrict__ tab_uni,
+                                                    double* __restrict__ z) {
+    const unsigned m = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long)gridDim.x * blockDim.x / G;
+    for (; r < a.n_rows; r += ngrp) {
+        const long long s = a.indptr[r], e = a.indptr[r + 1];
+        const double* tab = (e - s > 1) ? tab_amb : tab_uni;
+        double n0; int c0;
+        const double sum = row_numerators<G>(a, s, e, tab, m, lane, n0, c0);
+        const double rr = recip0(sum);
+        long long k = s + lane;
+        if (k < e) { z[k] = n0 * rr; k += G; }
+        for (; k < e; k += G) z[k] = (a.q[k] * __ldg(tab + a.col[k])) * rr;
+    }
+}
+
+// M-step accumulation from a caller-supplied z (model.py:730-733), for the tsc_mstep entry point
+template <int G>
+__global__ void __launch_bounds__(512) k_mstep_rows(Csr a, const double* __restrict__ wy, const double* __restrict__ z,
+                                                    double* __restrict__ acc, int K, int R) {
+    double* my = acc + (size_t)(blockIdx.x % R) * K;
+    const int lane = threadIdx.x & (G - 1);
+    long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long)gridDim.x * blockDim.x / G;
+    for (; r < a.n_rows; r += ngrp) {
+        const long long s = a.indptr[r], e = a.indptr[r + 1];
+        if (e - s < 2) continue;
+        const double w = wy[r];
+        for (long long k = s + lane; k < e; k += G) {
+            const double c = z[k] * w;
+            if (c != 0.0) atomicAdd(my + a.col[k], c);
+        }
+    }
+}
+
+// log-likelihood (model.py:744-760): sum_ij z_ij * log1p(Q_ij * pi_j * theta_j^Y_i).
+// z is either given (zin) or regenerated from the E-step tables (zamb/zuni).  Per-block partials, reduced in
+// fixed order by k_sum_partials.
+template <int G>
+__global__ void __launch_bounds__(512) k_lnl_rows(Csr a, const double* __restrict__ zin,
+                                                  const double* __restrict__ zamb, const double* __restrict__ zuni,
+                                                  const double* __restrict__ inner_amb, const double* __restrict__ inner_uni,
+                                                  double* __restrict__ partials, const EmState* __restrict__ st) {
+    __shared__ double s_red[32];
+    if (st && st->done) return;
+    const unsigned m = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long)gridDim.x * blockDim.x / G;
+    double local = 0;
+    for (; r < a.n_rows; r += ngrp) {
+        const long long s = a.indptr[r], e = a.indptr[r + 1];
+        const bool amb = (e - s) > 1;
+        const double* in = amb ? inner_amb : inner_uni;
+        if (zin) {
+            for (long long k = s + lane; k < e; k += G) {
+                const double zz = zin[k];
+                if (zz != 0.0) local += zz * log1p(a.q[k] * __ldg(in + a.col[k]));
+            }
+        } else {
+            const double* tab = amb ? zamb : zuni;
+            double n0; int c0;
+            const double sum = row_numerators<G>(a, s, e, tab, m, lane, n0, c0);
+            const double rr = recip0(sum);
+            for (long long k = s + lane; k < e; k += G) {
+                const int cc = a.col[k];
+                const double q = a.q[k];
+                const double zz = (q * __ldg(tab + cc)) * rr;
+                if (zz != 0.0) local += zz * log1p(q * __ldg(in + cc));
+            }
+        }
+    }
+    local = block_sum(local, s_red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = local;
+}
+
+__global__ void __launch_bounds__(1024) k_sum_partials(const double* __restrict__ partials, int n, double* __restrict__ out) {
+    __shared__ double s_red[32];
+    double v = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+    v = block_sum(v, s_red);
+    if (threadIdx.x == 0) *out = v;
+}
+
+// reassign (model.py:808-865, sparse_plus.py:99-165).  For each read: z from the E-step tables, best hits are the
+// stored (non-zero) entries equal to the row maximum (exact comparison, as sparse_plus.py:125).
+// Outputs, all optional: nbest per read, per-locus column sums (atomics), per-entry assignment values.
+struct ReassignArgs {
+    int method;
+    double thresh;
+    const int* picks;     // per read, TSC_CHOOSE only
+    int* nbest;           // per read
+    double* colsum;       // K
+    double* data;         // nnz
+};
+
+template <int G>
+__global__ void __launch_bounds__(512) k_reassign_rows(Csr a, const double* __restrict__ tab_amb, const double* __restrict__ tab_uni,
+                                                       ReassignArgs g) {
+    const unsigned m = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long)gridDim.x * blockDim.x / G;
+    for (; r < a.n_rows; r += ngrp) {
+        const long long s = a.indptr[r], e = a.indptr[r + 1];
+        const bool amb = (e - s) > 1;
+        const double* tab = amb ? tab_amb : tab_uni;
+        double n0; int c0;
+        const double sum = row_numerators<G>(a, s, e, tab, m, lane, n0, c0);
+        const double rr = recip0(sum);
+        // pass 2: row maximum of z and, for conf, the sum of the surviving entries
+        double zmax = 0, kept = 0;
+        for (long long k = s + lane; k < e; k += G) {
+            const double zz = (a.q[k] * __ldg(tab + a.col[k])) * rr;
+            zmax = fmax(zmax, zz);
+            if (zz >= g.thresh) kept += zz;
+        }
+        zmax = group_max<G>(zmax, m);
+        kept = group_sum<G>(kept, m);
+        // pass 3: number of best hits
+        int nb = 0;
+        for (long long k = s + lane; k < e; k += G) {
+            const double zz = (a.q[k] * __ldg(tab + a.col[k])) * rr;
+            nb += (zz == zmax && zz != 0.0);
+        }
+        nb = group_sum_int<G>(nb, m);
+        if (g.nbest && lane == 0) g.nbest[r] = nb;
+        if (!g.colsum && !g.data) continue;
+        const int pick = (g.method == 1 && g.picks && nb > 1) ? g.picks[r] : 0;
+        const double rkept = recip0(kept);
+        const double ravg = (nb > 0) ? 1.0 / (double)nb : 0.0;
+        int seen = 0;   // best hits before this chunk (row order)
+        const long long e_round = s + ((e - s + G - 1) / G) * G;
+        for (long long k = s + lane; k < e_round; k += G) {
+            const bool act = k < e;
+            int cc = 0; double zz = 0;
+            if (act) { cc = a.col[k]; zz = (a.q[k] * __ldg(tab + cc)) * rr; }
+            const bool best = act && zz == zmax && zz != 0.0;
+            double val = 0;
+            switch (g.method) {
+                case 0: val = (best && nb == 1) ? 1.0 : 0.0; break;
+                case 1: {
+                    const unsigned bal = (__ballot_sync(m, best) >> ((threadIdx.x & 31u) & ~(unsigned)(G - 1))) & GroupBits<G>::value;
+                    const int rank = seen + __popc(bal & ((1u << lane) - 1u));
+                    val = (best && (nb == 1 || rank == pick)) ? 1.0 : 0.0;
+                    seen += __popc(bal);
+                } break;
+                case 2: val = best ? ravg : 0.0; break;
+                case 3: val = (act && zz >= g.thresh) ? zz * rkept : 0.0; break;
+                case 4: val = (act && !amb) ? ceil(zz) : 0.0; break;
+                default: val = (act && zz > 0.0) ? 1.0 : 0.0; break;
+            }
+            if (act) {
+                if (g.data) g.data[k] = val;
+                if (g.colsum && val != 0.0) atomicAdd(g.colsum + cc, val);
+            }
+        }
+    }
+}
+
+// w per read for the API (model.py:690): wy for ambiguous reads, the single Q for unique ones; Y likewise
+__global__ void k_row_info(Csr a, const double* __restrict__ wy, uint8_t* __restrict__ y, double* __restrict__ w) {
+    long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; r < a.n_rows; r += (long long)gridDim.x * blockDim.x) {
+        const long long s = a.indptr[r], e = a.indptr[r + 1];
+        const bool amb = (e - s) > 1;
+        if (y) y[r] = amb ? 1 : 0;
+        if (w) w[r] = amb ? wy[r] : (e > s ? fmax(a.q[s], 0.0) : 0.0);
+    }
+}
+
+}  // namespace tsc

@@ -1,0 +1,310 @@
+# -*- coding: utf-8 -*-
+"""`TelescopeLikelihood` backed by libtelescope_b200.so -- same constructor, methods and attributes as the reference
+class (telescope/utils/model.py:631-865), with the EM loop, the posterior, the log-likelihood and the six
+reassignment modes running as CUDA kernels on B200.  There is no CPU path: constructing the class without the built
+library or without a GPU raises.
+
+What stays on the host, by design:
+  * the 65536-entry-at-most table Q(s) = expm1((s * (1/max_score)) * 100.) is evaluated with numpy exactly as
+    model.py:652-653 does, so the device Q is bit-identical to the reference's;
+  * `reassign('choose')` draws its tie-breaks from the global numpy RNG (the device reports how many best hits each
+    read has), so `np.random.seed(...)` in telescope_assign.run / telescope_resume.run keeps its meaning.
+"""
+import ctypes as C
+import logging as lg
+
+import numpy as np
+
+from . import _abi
+from .sparse_plus import csr_matrix_plus as csr_matrix
+from .sparse_plus import draw_picks
+
+_INT_DTYPE = {"exclude": np.int8, "choose": np.int8, "unique": np.uint8, "all": np.uint8}
+
+
+class DistInfo(object):
+    """How this process takes part in a multi-process run (one process per GPU, e.g. under torchrun)."""
+
+    def __init__(self, n_procs=1, proc_rank=0, nccl_id=None):
+        self.n_procs, self.proc_rank, self.nccl_id = n_procs, proc_rank, nccl_id
+
+
+class TelescopeLikelihood(object):
+
+    def __init__(self, score_matrix, opts, devices=None, dist=None, max_score=None, kernel="auto", replicas=0,
+                 smem_table_cols=-1, permute_columns=True):
+        """score_matrix: csr_matrix (uint16) N reads x K loci; opts: em_epsilon, max_iter, pi_prior, theta_prior.
+
+        devices: list of CUDA ordinals driven from this process (default [0]).  dist: DistInfo when this process
+        holds only its block of reads; `max_score` must then be the global maximum score.
+        """
+        self._lib = _abi.load()
+        self._h = None
+        self.raw_scores = score_matrix
+        if score_matrix.nnz >= 2 ** 31 and score_matrix.indptr.dtype != np.int64:
+            raise ValueError("indptr must be int64 for >= 2^31 entries")
+        self.max_score = score_matrix.max() if max_score is None else max_score        # model.py:640
+        self.N, self.K = score_matrix.shape                                               # model.py:643
+        self.scale_factor = 100.                                                          # model.py:652
+        ms = int(self.max_score)
+        if ms <= 0:
+            raise ValueError("score matrix has no positive scores")
+        # Q lookup table, evaluated as the reference evaluates Q (model.py:653, sparse_plus.py:89-91)
+        self._lut = np.expm1((np.arange(ms + 1, dtype=np.float64) * (1. / ms)) * self.scale_factor)
+
+        self.epsilon = opts.em_epsilon                                                    # model.py:661-662
+        self.max_iter = opts.max_iter
+        self.pi = np.repeat(1. / self.K, self.K)                                          # model.py:667
+        self.pi_init = None
+        self.theta = np.repeat(1. / self.K, self.K)                                       # model.py:673
+        self.theta_init = None
+        self.lnl = float('inf')                                                           # model.py:683
+        self.pi_prior = opts.pi_prior                                                     # model.py:686-687
+        self.theta_prior = opts.theta_prior
+        self._z = None
+        self._z_stale = True
+        self._Q = None
+        self._Y = None
+        self._w = None
+        self.diffs = []
+        self.lnls = []
+        self.n_iter = 0
+        self.converged = False
+
+        indptr = np.ascontiguousarray(score_matrix.indptr)
+        if indptr.dtype not in (np.int32, np.int64):
+            indptr = indptr.astype(np.int64)
+        indices = np.ascontiguousarray(score_matrix.indices, dtype=np.int32)
+        raw = np.ascontiguousarray(score_matrix.data, dtype=np.uint16)
+        if raw.size and not np.array_equal(raw, score_matrix.data):
+            raise ValueError("scores must be integers in [0, 65535] (the reference stores uint16, model.py:300)")
+        self._indptr, self._indices = indptr, indices
+
+        cfg = _abi.TscConfig()
+        self._lib.tsc_config_default(C.byref(cfg))
+        devices = [0] if devices is None else list(devices)
+        self._dev_arr = (C.c_int32 * len(devices))(*devices)
+        cfg.n_local_devices = len(devices)
+        cfg.device_ids = C.cast(self._dev_arr, C.POINTER(C.c_int32))
+        self._nccl_id = None
+        if dist is not None and dist.n_procs > 1:
+            cfg.n_procs, cfg.proc_rank = dist.n_procs, dist.proc_rank
+            self._nccl_id = C.create_string_buffer(dist.nccl_id, 128)
+            cfg.nccl_id = C.cast(self._nccl_id, C.c_void_p)
+        if len(devices) > 1 or (dist is not None and dist.n_procs > 1):
+            path = _abi.find_nccl()
+            if path:
+                self._lib.tsc_set_nccl_path(path.encode())
+        cfg.kernel = _abi.KERNELS[kernel]
+        cfg.replicas = replicas
+        cfg.smem_table_cols = smem_table_cols
+        cfg.permute_columns = 1 if permute_columns else 0
+        h = C.c_void_p()
+        _abi.check(self._lib.tsc_create(
+            C.byref(h), C.byref(cfg), self.N, self.K, int(indices.size),
+            indptr.ctypes.data_as(C.c_void_p), indptr.dtype.itemsize, _abi._p(indices, C.c_int32),
+            _abi._p(raw, C.c_uint16), _abi._p(self._lut, C.c_double), int(self._lut.size),
+            float(self.pi_prior), float(self.theta_prior)))
+        self._h = h
+
+        sc = np.zeros(5)
+        pisum0 = np.zeros(self.K)
+        _abi.check(self._lib.tsc_get_constants(self._h, _abi._p(sc, C.c_double), _abi._p(pisum0, C.c_double)))
+        self._total_wt, self._ambig_wt, self._max_wt = sc[0], sc[1], sc[2]                # model.py:691-692
+        self._unique_wt = self._total_wt - self._ambig_wt                                 # model.py:693
+        self._pi_prior_wt, self._theta_prior_wt = sc[3], sc[4]                            # model.py:696-697
+        self._pisum0 = np.asmatrix(pisum0)                                                # model.py:699
+        lg.debug('done initializing model')
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tsc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ lazily materialised attributes
+    def _wrap(self, data, dtype=None):
+        if dtype is not None:
+            data = data.astype(dtype)
+        return csr_matrix((data, self._indices.copy(), self._indptr.copy()), shape=(self.N, self.K))
+
+    @property
+    def Q(self):
+        if self._Q is None:
+            q = np.empty(self._indices.size)
+            _abi.check(self._lib.tsc_get_q(self._h, _abi._p(q, C.c_double)))
+            self._Q = self._wrap(q)
+        return self._Q
+
+    def _row_info(self):
+        if self._Y is None:
+            y = np.zeros(self.N, dtype=np.uint8)
+            w = np.zeros(self.N)
+            _abi.check(self._lib.tsc_get_row_info(self._h, _abi._p(y, C.c_uint8), _abi._p(w, C.c_double)))
+            self._Y, self._w = y.reshape(-1, 1), w
+        return self._Y, self._w
+
+    @property
+    def Y(self):
+        return self._row_info()[0]
+
+    @property
+    def _weights(self):
+        import scipy.sparse
+        return scipy.sparse.coo_matrix(self._row_info()[1].reshape(-1, 1))
+
+    @property
+    def _yslice(self):
+        return self.Y[:, 0].nonzero()[0]
+
+    @property
+    def z(self):
+        """Posterior of the last E-step (model.py:795).  Pulled from the device on first access."""
+        if self.n_iter == 0:
+            return None
+        if self._z_stale:
+            d = np.empty(self._indices.size)
+            _abi.check(self._lib.tsc_get_z(self._h, 0, _abi._p(d, C.c_double)))
+            self._z = self._finish_z(d)
+            self._z_stale = False
+        return self._z
+
+    def _finish_z(self, data):
+        z = self._wrap(data)
+        z.eliminate_zeros()          # the reference's sparse add drops exact zeros (model.py:720)
+        return z
+
+    def _entry_data(self, m):
+        """Data of a matrix whose structure is a subset of raw_scores', expanded to raw_scores' entry order."""
+        m = csr_matrix(m)
+        if m.shape != (self.N, self.K):
+            raise ValueError("matrix shape %s does not match (%d, %d)" % (m.shape, self.N, self.K))
+        if m.nnz == self._indices.size and np.array_equal(m.indptr, self._indptr) and np.array_equal(m.indices, self._indices):
+            return np.ascontiguousarray(m.data, dtype=np.float64)
+        m.sort_indices()
+        K = np.int64(self.K)
+        full = np.repeat(np.arange(self.N, dtype=np.int64), np.diff(self._indptr)) * K + self._indices
+        sub = np.repeat(np.arange(self.N, dtype=np.int64), np.diff(m.indptr)) * K + m.indices
+        pos = np.searchsorted(full, sub)
+        if pos.size and (pos.max() >= full.size or not np.array_equal(full[pos], sub)):
+            raise ValueError("matrix has entries outside the score matrix's structure")
+        out = np.zeros(full.size)
+        out[pos] = m.data
+        return out
+
+    # ------------------------------------------------------------------ model.py:702-760
+    def estep(self, pi, theta):
+        lg.debug('started e-step')
+        pi, theta = _abi.as_f64(pi), _abi.as_f64(theta)
+        d = np.empty(self._indices.size)
+        _abi.check(self._lib.tsc_estep(self._h, _abi._p(pi, C.c_double), _abi._p(theta, C.c_double), _abi._p(d, C.c_double)))
+        return self._finish_z(d)
+
+    def mstep(self, z):
+        lg.debug('started m-step')
+        zd = self._entry_data(z)
+        pi_hat, theta_hat = np.empty(self.K), np.empty(self.K)
+        _abi.check(self._lib.tsc_mstep(self._h, _abi._p(zd, C.c_double), _abi._p(pi_hat, C.c_double), _abi._p(theta_hat, C.c_double)))
+        return pi_hat, theta_hat
+
+    def calculate_lnl(self, z, pi, theta):
+        lg.debug('started lnl')
+        zd = self._entry_data(z)
+        pi, theta = _abi.as_f64(pi), _abi.as_f64(theta)
+        out = C.c_double(0)
+        _abi.check(self._lib.tsc_calculate_lnl(self._h, _abi._p(zd, C.c_double), _abi._p(pi, C.c_double),
+                                                _abi._p(theta, C.c_double), C.byref(out)))
+        lg.debug('completed lnl')
+        return out.value
+
+    # ------------------------------------------------------------------ model.py:762-806
+    def em(self, use_likelihood=False, loglev=lg.WARNING, save_memory=True):
+        msgD = 'Iteration {:d}, diff={:.5g}'
+        msgL = 'Iteration {:d}, lnl= {:.5e}, diff={:.5g}'
+        T = max(1, int(self.max_iter))
+        # the device loop continues from the current self.pi / self.theta (model.py:773)
+        pi, theta = _abi.as_f64(self.pi), _abi.as_f64(self.theta)
+        _abi.check(self._lib.tsc_set_params(self._h, _abi._p(pi, C.c_double), _abi._p(theta, C.c_double)))
+        diffs, lnls = np.zeros(T), np.zeros(T)
+        n_iter, conv, lnl = C.c_int32(0), C.c_int32(0), C.c_double(0)
+        _abi.check(self._lib.tsc_em(self._h, T, float(self.epsilon), 1 if use_likelihood else 0,
+                                     _abi._p(diffs, C.c_double), _abi._p(lnls, C.c_double),
+                                     C.byref(n_iter), C.byref(conv), C.byref(lnl)))
+        inum, converged = n_iter.value, bool(conv.value)
+        self.diffs, self.lnls = diffs[:inum].tolist(), (lnls[:inum].tolist() if use_likelihood else [])
+        for i in range(inum):
+            if use_likelihood:
+                lg.log(loglev, msgL.format(i + 1, lnls[i], diffs[i]))
+            else:
+                lg.log(loglev, msgD.format(i + 1, diffs[i]))
+        pi, theta, pi0, theta0 = (np.empty(self.K) for _ in range(4))
+        _abi.check(self._lib.tsc_get_params(self._h, *(_abi._p(a, C.c_double) for a in (pi, theta, pi0, theta0))))
+        self.pi, self.theta = pi, theta
+        self.pi_init, self.theta_init = pi0, theta0                                     # model.py:776-778
+        self.lnl = lnl.value
+        self.n_iter, self.converged = inum, converged
+        self._z_stale = True
+        _con = 'converged' if converged else 'terminated'
+        lg.log(loglev, 'EM {:s} after {:d} iterations.'.format(_con, inum))
+        lg.log(loglev, 'Final log-likelihood: {:f}.'.format(self.lnl))
+        return
+
+    def kernel_times_ms(self):
+        n = C.c_int32(0)
+        buf = np.zeros(max(1, self.n_iter), dtype=np.float32)
+        _abi.check(self._lib.tsc_get_kernel_times(self._h, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size, C.byref(n)))
+        return buf[:min(n.value, buf.size)]
+
+    def counters(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        _abi.check(self._lib.tsc_get_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
+
+    # ------------------------------------------------------------------ model.py:808-865
+    def _check_method(self, method):
+        if method not in ['exclude', 'choose', 'average', 'conf', 'unique', 'all']:
+            raise ValueError('Argument "method" should be one of (exclude, choose, average, conf, unique, all)')
+        return _abi.METHODS[method]
+
+    def _picks(self, method, initial):
+        """Tie-breaks for 'choose': one draw per read with more than one best hit, in read order."""
+        if method != 'choose':
+            return None
+        nbest = np.zeros(self.N, dtype=np.int32)
+        _abi.check(self._lib.tsc_reassign_nbest(self._h, 1 if initial else 0, _abi._p(nbest, C.c_int32)))
+        picks = np.zeros(self.N, dtype=np.int32)
+        ties = np.flatnonzero(nbest > 1)
+        picks[ties] = draw_picks(nbest[ties])
+        return picks
+
+    def reassign(self, method, thresh=0.9, initial=False):
+        """Assignment matrix, as the reference returns it (int8 / uint8 / float64 csr_matrix)."""
+        m = self._check_method(method)
+        picks = self._picks(method, initial)
+        d = np.empty(self._indices.size)
+        _abi.check(self._lib.tsc_reassign_data(self._h, m, float(thresh), 1 if initial else 0,
+                                                _abi._p(picks, C.c_int32) if picks is not None else None,
+                                                _abi._p(d, C.c_double)))
+        out = self._wrap(d, _INT_DTYPE.get(method))
+        out.eliminate_zeros()
+        return out
+
+    def reassign_colsum(self, method, thresh=0.9, initial=False):
+        """`reassign(method, thresh, initial).sum(0).A1` without moving the N x K matrix off the device."""
+        m = self._check_method(method)
+        picks = self._picks(method, initial)
+        out = np.empty(self.K)
+        _abi.check(self._lib.tsc_reassign_colsum(self._h, m, float(thresh), 1 if initial else 0,
+                                                  _abi._p(picks, C.c_int32) if picks is not None else None,
+                                                  _abi._p(out, C.c_double)))
+        if method in ('exclude', 'choose'):
+            return np.rint(out).astype(np.int64)      # scipy sums int8 into int64
+        if method in ('unique', 'all'):
+            return np.rint(out).astype(np.uint64)     # and uint8 into uint64
+        return out

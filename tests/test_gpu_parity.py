@@ -1,0 +1,227 @@
+"""GPU parity: libtelescope_b200 (through the C ABI / the TelescopeLikelihood class) against the CPU oracle
+(oracle/em_numpy.py, itself pinned to the reference by tests/test_oracle.py) on the same seeded inputs.
+
+Tolerances: bit-exact for Q, Y and every integer reassignment count; 1e-6 relative (BASELINE.json north_star) for
+pi, theta, posteriors z and the log-likelihood -- the only differences are summation order in the row sums
+(warp tree vs sequential) and in the per-locus M-step sums (atomics vs row order).  In practice they agree to
+~1e-12, which the tests also assert where it is robust.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import Opts, rel_err
+from oracle.em_numpy import EMOracle
+from telescope_b200.synthetic import synth_csr
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6          # the contract
+TIGHT = 1e-9         # what summation-order differences actually allow
+
+
+def _matrix(N, K, avg, skew, seed):
+    ip, ix, raw = synth_csr(N, K, avg, skew, seed)
+    return sp.csr_matrix((raw, ix, ip), shape=(N, K))
+
+
+def _tl(m, opts, **kw):
+    from telescope_b200.likelihood import TelescopeLikelihood
+    return TelescopeLikelihood(m, opts, **kw)
+
+
+def _oracle(m, opts):
+    return EMOracle(m.indptr, m.indices, m.data, m.shape[1], opts.em_epsilon, opts.max_iter, opts.pi_prior, opts.theta_prior)
+
+
+def _dense_z(tl_z, m):
+    """z as entry-order data with explicit zeros."""
+    out = np.zeros(m.nnz)
+    z = sp.csr_matrix(tl_z)
+    z.sort_indices()
+    K = np.int64(m.shape[1])
+    full = np.repeat(np.arange(m.shape[0], dtype=np.int64), np.diff(m.indptr)) * K + m.indices
+    sub = np.repeat(np.arange(m.shape[0], dtype=np.int64), np.diff(z.indptr)) * K + z.indices
+    out[np.searchsorted(full, sub)] = z.data
+    return out
+
+
+CASES = [
+    dict(N=3000, K=97, avg=6, skew=False, seed=11),
+    dict(N=20000, K=1500, avg=20, skew=False, seed=12),
+    dict(N=8000, K=700, avg=20, skew=True, seed=13),       # Zipf rows, some > 128 entries (long-row path)
+    dict(N=5000, K=40, avg=3, skew=False, seed=14),        # short reads, tiny K
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_construction_matches_oracle(case):
+    m = _matrix(**case)
+    opts = Opts()
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    assert np.array_equal(tl.Q.data, o.Q), "Q must be bit-identical (host LUT, model.py:653)"
+    assert np.array_equal(tl.Y.ravel(), o.Y)
+    assert np.array_equal(tl._row_info()[1], o.weights)
+    assert abs(tl._total_wt - o.total_wt) <= 1e-12 * o.total_wt
+    assert abs(tl._ambig_wt - o.ambig_wt) <= 1e-12 * o.ambig_wt
+    assert tl._max_wt == o.weights.max()
+    assert tl._theta_prior_wt == o.theta_prior_wt and tl._pi_prior_wt == o.pi_prior_wt
+    assert rel_err(np.asarray(tl._pisum0).ravel(), o.pisum0) < 1e-12
+    tl.close()
+
+
+@pytest.mark.parametrize("case", CASES[:3])
+def test_single_steps_match_oracle(case):
+    m = _matrix(**case)
+    opts = Opts()
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    rng = np.random.default_rng(5)
+    pi = rng.random(m.shape[1]); pi /= pi.sum()
+    theta = rng.random(m.shape[1]); theta /= theta.sum()
+    pi[::7] = 0.0                                           # zero proportions: entries vanish from z (model.py:720)
+    z_o = o.estep(pi, theta)
+    z_g = tl.estep(pi, theta)
+    assert z_g.nnz == np.count_nonzero(z_o), "exact zeros are dropped like scipy's sparse add does"
+    assert rel_err(_dense_z(z_g, m), z_o) < TIGHT
+    pi_o, th_o = o.mstep(z_o)
+    z_in = sp.csr_matrix((z_o.copy(), m.indices.copy(), m.indptr.copy()), shape=m.shape)
+    pi_g, th_g = tl.mstep(z_in)
+    assert rel_err(pi_g, pi_o) < TIGHT and rel_err(th_g, th_o) < TIGHT
+    z_in.eliminate_zeros()                                  # structure is now a strict subset of raw_scores'
+    pi_g2, th_g2 = tl.mstep(z_in)
+    assert rel_err(pi_g2, pi_o) < TIGHT and rel_err(th_g2, th_o) < TIGHT
+    l_o = o.calculate_lnl(z_o, pi_o, th_o)
+    l_g = tl.calculate_lnl(z_in, pi_o, th_o)
+    assert abs(l_g - l_o) <= TIGHT * abs(l_o)
+    tl.close()
+
+
+@pytest.mark.parametrize("kernel", ["rows", "tiles"])
+@pytest.mark.parametrize("case", CASES)
+def test_em_matches_oracle(case, kernel):
+    m = _matrix(**case)
+    opts = Opts(max_iter=25)
+    tl, o = _tl(m, opts, kernel=kernel), _oracle(m, opts)
+    tl.em()
+    o.em()
+    assert tl.n_iter == o.n_iter and tl.converged == o.converged
+    assert rel_err(tl.diffs, o.diffs) < RTOL
+    assert rel_err(tl.pi, o.pi) < RTOL and rel_err(tl.theta, o.theta) < RTOL
+    assert rel_err(tl.pi_init, o.pi_init) < TIGHT and rel_err(tl.theta_init, o.theta_init) < TIGHT
+    assert abs(tl.lnl - o.lnl) <= RTOL * abs(o.lnl)
+    assert rel_err(_dense_z(tl.z, m), o.z) < RTOL
+    # tighter: what we actually expect from reordered fp64 sums
+    assert rel_err(tl.pi, o.pi) < 1e-8 and abs(tl.lnl - o.lnl) <= 1e-10 * abs(o.lnl)
+    for method, initial in [("conf", False), ("all", True), ("unique", False), ("exclude", True), ("average", True),
+                            ("exclude", False), ("all", False), ("average", False), ("conf", True), ("unique", True)]:
+        a = tl.reassign_colsum(method, 0.9, initial)
+        b = o.reassign_colsum(method, 0.9, initial)
+        if a.dtype.kind in "iu":
+            assert np.array_equal(a, b), (method, initial)
+        else:
+            assert rel_err(a, b) < RTOL, (method, initial)
+    tl.close()
+
+
+def test_choose_uses_numpy_rng_like_reference():
+    m = _matrix(N=4000, K=300, avg=8, skew=False, seed=21)
+    opts = Opts(max_iter=5)
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    tl.em(); o.em()
+    for initial in (True, False):
+        np.random.seed(1234)
+        a = tl.reassign_colsum("choose", 0.9, initial)
+        np.random.seed(1234)
+        b = o.reassign_colsum("choose", 0.9, initial)
+        assert np.array_equal(a, b)
+        np.random.seed(99)
+        ma = tl.reassign("choose", 0.9, initial)
+        np.random.seed(99)
+        db = o.reassign_data("choose", 0.9, initial)
+        assert ma.dtype == np.int8
+        assert np.array_equal(np.asarray(ma.sum(0)).ravel(), np.bincount(m.indices, weights=db, minlength=m.shape[1]).astype(np.int64))
+    tl.close()
+
+
+def test_reassign_matrices_match_oracle():
+    m = _matrix(N=3000, K=97, avg=6, skew=False, seed=11)
+    opts = Opts(max_iter=10)
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    tl.em(); o.em()
+    for method in ("exclude", "average", "conf", "unique", "all"):
+        for initial in (False, True):
+            a = tl.reassign(method, 0.9, initial)
+            b = o.reassign_data(method, 0.9, initial)
+            assert a.dtype == b.dtype, (method, a.dtype, b.dtype)
+            bm = sp.csr_matrix((b, m.indices.copy(), m.indptr.copy()), shape=m.shape)
+            bm.eliminate_zeros()
+            assert a.nnz == bm.nnz
+            d = abs(a.astype(np.float64) - bm.astype(np.float64))
+            assert (d.max() if d.nnz else 0.0) < 1e-9, (method, initial)
+    with pytest.raises(ValueError):
+        tl.reassign("best")
+    tl.close()
+
+
+def test_use_likelihood_and_priors():
+    m = _matrix(N=6000, K=200, avg=10, skew=False, seed=31)
+    opts = Opts(max_iter=12, pi_prior=3, theta_prior=7, em_epsilon=1e-3)
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    tl.em(use_likelihood=True)
+    o.em(use_likelihood=True)
+    assert tl.n_iter == o.n_iter and tl.converged == o.converged
+    assert rel_err(tl.lnls, o.lnls) < RTOL and rel_err(tl.diffs, o.diffs) < RTOL
+    assert abs(tl.lnl - o.lnl) <= RTOL * abs(o.lnl)
+    assert rel_err(tl.pi, o.pi) < RTOL and rel_err(tl.theta, o.theta) < RTOL
+    tl.close()
+
+
+def test_edge_shapes():
+    # empty reads, a read covering every locus, a single-read matrix, all-unique reads
+    K = 12
+    rows = [[], [3], [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11], [], [5, 7], [7], []]
+    indptr = np.cumsum([0] + [len(r) for r in rows])
+    indices = np.concatenate([np.array(r, dtype=np.int32) for r in rows]).astype(np.int32)
+    raw = (150 + (np.arange(indices.size) * 7) % 60).astype(np.uint16)
+    m = sp.csr_matrix((raw, indices, indptr), shape=(len(rows), K))
+    opts = Opts(max_iter=6)
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    tl.em(); o.em()
+    assert tl.n_iter == o.n_iter
+    assert rel_err(tl.pi, o.pi) < TIGHT and rel_err(tl.theta, o.theta) < TIGHT
+    assert abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
+    assert np.array_equal(tl.Y.ravel(), o.Y)
+    for method in ("exclude", "unique", "all"):
+        assert np.array_equal(tl.reassign_colsum(method), o.reassign_colsum(method))
+    tl.close()
+    # all reads unique: theta's denominator is only the prior
+    m2 = sp.csr_matrix((np.array([200, 180, 190], dtype=np.uint16), np.array([1, 0, 1], dtype=np.int32), np.array([0, 1, 2, 3])), shape=(3, 4))
+    tl, o = _tl(m2, opts), _oracle(m2, opts)
+    tl.em(); o.em()
+    assert tl.n_iter == o.n_iter and rel_err(tl.pi, o.pi) < TIGHT and rel_err(tl.theta, o.theta) < TIGHT
+    tl.close()
+
+
+def test_rows_and_tiles_kernels_agree_at_scale():
+    m = _matrix(N=400000, K=5000, avg=20, skew=True, seed=41)
+    opts = Opts(max_iter=8, em_epsilon=-1)
+    a, b = _tl(m, opts, kernel="rows"), _tl(m, opts, kernel="tiles")
+    a.em(); b.em()
+    assert a.n_iter == b.n_iter == 8
+    assert rel_err(a.pi, b.pi) < 1e-9 and rel_err(a.theta, b.theta) < 1e-9
+    assert abs(a.lnl - b.lnl) <= 1e-10 * abs(a.lnl)
+    a.close(); b.close()
+
+
+def test_multi_gpu_in_process_matches_single():
+    from telescope_b200 import _abi
+    if _abi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    m = _matrix(N=100000, K=3000, avg=20, skew=False, seed=51)
+    opts = Opts(max_iter=10)
+    a, b = _tl(m, opts), _tl(m, opts, devices=[0, 1])
+    a.em(); b.em()
+    assert a.n_iter == b.n_iter
+    assert rel_err(a.pi, b.pi) < 1e-9 and abs(a.lnl - b.lnl) <= 1e-10 * abs(a.lnl)
+    assert np.array_equal(a.reassign_colsum("exclude"), b.reassign_colsum("exclude"))
+    a.close(); b.close()

@@ -79,6 +79,9 @@ int tsc_device_count(int32_t* n_out);
 int tsc_set_nccl_path(const char* path);
 int tsc_nccl_unique_id(void* out128);
 void tsc_config_default(tsc_config* cfg);
+/* page-locked host memory for the CSR arrays (optional; uploads from it run at full PCIe speed) */
+void* tsc_pinned_alloc(uint64_t bytes);
+void tsc_pinned_free(void* p);
 
 /*
  * TelescopeLikelihood.__init__ (model.py:635-700).
@@ -114,7 +117,10 @@ int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_likelihood,
            double* diffs_out, double* lnls_out, int32_t* n_iter, int32_t* converged, double* final_lnl);
 /* per-iteration device time (ms, CUDA events) of the fused E+M kernel of the last tsc_em on local shard 0 */
 int tsc_get_kernel_times(tsc_handle* h, float* ms_out, int32_t max_n, int32_t* n_out);
-/* which = 0: the fused E+M kernel of tsc_em.  launches = kernels this library launched since creation. */
+/* device time (ms, CUDA events on the library's stream of local shard 0) of the whole last tsc_em loop, first
+ * kernel to the final log-likelihood reduction */
+int tsc_get_em_device_ms(tsc_handle* h, float* ms_out);
+/* launches = kernels this library launched since creation; bytes moved over PCIe by this handle */
 int tsc_get_counters(tsc_handle* h, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
 /* pi, theta, pi_init, theta_init (model.py:777-778,796); any pointer may be NULL */

@@ -22,7 +22,7 @@ SYMBOLS = (
     "tsc_config_default", "tsc_create", "tsc_destroy", "tsc_get_constants", "tsc_get_row_info", "tsc_get_q",
     "tsc_em", "tsc_get_kernel_times", "tsc_get_counters", "tsc_get_params", "tsc_set_params", "tsc_estep",
     "tsc_mstep", "tsc_calculate_lnl", "tsc_get_z", "tsc_reassign_nbest", "tsc_reassign_colsum",
-    "tsc_reassign_data",
+    "tsc_reassign_data", "tsc_get_em_device_ms", "tsc_pinned_alloc", "tsc_pinned_free",
 )
 
 
@@ -81,6 +81,11 @@ def load():
     lib.tsc_get_q.argtypes = [vp, dp]
     lib.tsc_em.argtypes = [vp, i32, dbl, i32, dp, dp, ip, ip, dp]
     lib.tsc_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), i32, ip]
+    lib.tsc_get_em_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.tsc_pinned_alloc.argtypes = [C.c_uint64]
+    lib.tsc_pinned_alloc.restype = C.c_void_p
+    lib.tsc_pinned_free.argtypes = [vp]
+    lib.tsc_pinned_free.restype = None
     lib.tsc_get_counters.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.tsc_get_params.argtypes = [vp, dp, dp, dp, dp]
     lib.tsc_set_params.argtypes = [vp, dp, dp]
@@ -142,3 +147,26 @@ def nccl_unique_id():
 
 def as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class PinnedArray(object):
+    """numpy array over page-locked host memory (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        self._ptr = self._lib.tsc_pinned_alloc(max(1, n * dtype.itemsize))
+        if not self._ptr:
+            raise TelescopeCudaError(self._lib.tsc_last_error().decode())
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self.array = None
+                self._lib.tsc_pinned_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass

@@ -125,6 +125,7 @@ struct Shard {
     ncclComm_t comm = nullptr;
     cudaEvent_t ev_poll[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_k;   // 2 per iteration, shard 0 only
+    cudaEvent_t ev_em[2] = {nullptr, nullptr};
     int n_sm = 0;
     int grid_rows = 0, grid_tiles = 0;
     size_t smem_tiles = 0;
@@ -145,6 +146,7 @@ struct tsc_handle {
     int n_iter = 0, converged = 0;
     double lnl = std::numeric_limits<double>::infinity();
     std::vector<float> kernel_ms;
+    float em_ms = 0.f;
     long long launches = 0, h2d = 0, d2h = 0;
 };
 
@@ -298,6 +300,7 @@ static void free_shard(Shard& s) {
     if (s.st_host) cudaFreeHost(s.st_host);
     for (auto& e : s.ev_poll) if (e) cudaEventDestroy(e);
     for (auto& e : s.ev_k) if (e) cudaEventDestroy(e);
+    for (auto& e : s.ev_em) if (e) cudaEventDestroy(e);
     if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Shard();
@@ -679,6 +682,20 @@ extern "C" int tsc_get_counters(tsc_handle* h, int64_t* launches, int64_t* h2d_b
     return TSC_OK;
 }
 
+extern "C" int tsc_get_em_device_ms(tsc_handle* h, float* ms_out) {
+    if (!h || !ms_out) return fail(TSC_ERR_ARG, "NULL argument");
+    *ms_out = h->em_ms;
+    return TSC_OK;
+}
+
+extern "C" void* tsc_pinned_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { fail(TSC_ERR_ALLOC, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+extern "C" void tsc_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" int tsc_get_kernel_times(tsc_handle* h, float* ms_out, int32_t max_n, int32_t* n_out) {
     if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
     const int n = (int)std::min<size_t>(h->kernel_ms.size(), (size_t)std::max(max_n, 0));
@@ -762,6 +779,8 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
         CU(cudaEventCreate(&e));
         s0.ev_k.push_back(e);
     }
+    if (!s0.ev_em[0]) { CU(cudaEventCreate(&s0.ev_em[0])); CU(cudaEventCreate(&s0.ev_em[1])); }
+    CU(cudaEventRecord(s0.ev_em[0], s0.stream));
     const int poll_every = 4;
     int issued = 0, polls = 0;
     bool stop = false;
@@ -835,6 +854,10 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
         rc = sync_all(h);
         if (rc) return rc;
     }
+    CU(cudaSetDevice(s0.dev));
+    CU(cudaEventRecord(s0.ev_em[1], s0.stream));
+    CU(cudaEventSynchronize(s0.ev_em[1]));
+    CU(cudaEventElapsedTime(&h->em_ms, s0.ev_em[0], s0.ev_em[1]));
     if (diffs_out) CU(cudaMemcpy(diffs_out, s0.diffs, sizeof(double) * fin.iter, cudaMemcpyDeviceToHost));
     if (lnls_out && use_likelihood) CU(cudaMemcpy(lnls_out, s0.lnls, sizeof(double) * fin.iter, cudaMemcpyDeviceToHost));
     h->d2h += sizeof(double) * fin.iter * (use_likelihood ? 2 : 1) + sizeof(EmState);

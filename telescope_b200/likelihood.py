@@ -76,7 +76,7 @@ class TelescopeLikelihood(object):
             indptr = indptr.astype(np.int64)
         indices = np.ascontiguousarray(score_matrix.indices, dtype=np.int32)
         raw = np.ascontiguousarray(score_matrix.data, dtype=np.uint16)
-        if raw.size and not np.array_equal(raw, score_matrix.data):
+        if score_matrix.data.dtype != np.uint16 and raw.size and not np.array_equal(raw, score_matrix.data):
             raise ValueError("scores must be integers in [0, 65535] (the reference stores uint16, model.py:300)")
         self._indptr, self._indices = indptr, indices
 
@@ -260,6 +260,11 @@ class TelescopeLikelihood(object):
         buf = np.zeros(max(1, self.n_iter), dtype=np.float32)
         _abi.check(self._lib.tsc_get_kernel_times(self._h, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size, C.byref(n)))
         return buf[:min(n.value, buf.size)]
+
+    def em_device_ms(self):
+        ms = C.c_float(0)
+        _abi.check(self._lib.tsc_get_em_device_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def counters(self):
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)

@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--smem-table-cols", type=int, default=-1)
     ap.add_argument("--cpu-seconds", type=float, default=25.0, help="CPU baseline budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--permute", action="store_true", help="renumber loci by descending entry count on the device")
     return ap.parse_args()
 
 
@@ -274,7 +275,7 @@ def main():
     total_nnz = int(sum_over_ranks(float(local_nnz)))
 
     kw = dict(devices=[local_rank], dist=dist, max_score=max_score, kernel=a.kernel, replicas=a.replicas,
-              smem_table_cols=a.smem_table_cols)
+              smem_table_cols=a.smem_table_cols, permute_columns=a.permute)
 
     # ---- e2e: the whole job through the public class, host buffers in, parameters out
     barrier()

@@ -67,7 +67,8 @@ typedef struct {
     int32_t replicas;          /* copies of the per-locus accumulator in L2 (0 = auto) */
     int32_t smem_table_cols;   /* loci whose pi*theta entry is staged in shared memory (-1 = auto) */
     int32_t smem_acc_cols;     /* loci accumulated in shared memory before flushing (-1 = auto) */
-    int32_t permute_columns;   /* 1 = renumber loci by descending entry count internally (default), 0 = keep */
+    int32_t permute_columns;   /* 1 = renumber loci by descending entry count internally, 0 = keep the caller's
+                                  numbering (default: neighbouring loci share sectors, which the scatter-add likes) */
     int32_t reserved[6];
 } tsc_config;
 

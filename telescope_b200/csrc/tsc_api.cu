@@ -218,16 +218,14 @@ static void build_tiles(const long long* ip, long long n_rows, std::vector<Tile>
     out.reserve((size_t)(ip[n_rows] / 100 + 16));
     long long r = 0;
     while (r < n_rows) {
-        const long long lo = ip[r];
-        const long long base = lo & ~3LL;
-        const int first = (int)(lo - base);
+        const long long base = ip[r];
         Tile t;
         t.base = base;
         t.row0 = (int)r;
         t.flags[0] = t.flags[1] = t.flags[2] = t.flags[3] = 0;
         if (ip[r + 1] - base > 128) {   // long read
-            const long long len = ip[r + 1] - lo;
-            t.meta = (first << 8) | (1 << 16);
+            const long long len = ip[r + 1] - base;
+            t.meta = (1 << 16);
             t.flags[0] = (unsigned)(len & 0xffffffffLL);
             t.flags[1] = (unsigned)(len >> 32);
             out.push_back(t);
@@ -236,14 +234,14 @@ static void build_tiles(const long long* ip, long long n_rows, std::vector<Tile>
             continue;
         }
         long long r2 = r;
-        while (r2 < n_rows && ip[r2 + 1] - base <= 128 && (r2 - r) < 128) {
+        while (r2 < n_rows && ip[r2 + 1] - base <= 128) {
             const int p = (int)(ip[r2] - base);
             t.flags[p >> 5] |= 1u << (p & 31);
             ++r2;
         }
         const int end = (int)(ip[r2] - base);
         if (end < 128) t.flags[end >> 5] |= 1u << (end & 31);
-        t.meta = (end & 0xff) | (first << 8) | ((int)(r2 - r) << 16);
+        t.meta = (end & 0xff) | ((int)(r2 - r) << 16);
         out.push_back(t);
         r = r2;
     }
@@ -287,7 +285,7 @@ extern "C" void tsc_config_default(tsc_config* cfg) {
     cfg->replicas = 0;
     cfg->smem_table_cols = -1;
     cfg->smem_acc_cols = -1;
-    cfg->permute_columns = 1;
+    cfg->permute_columns = 0;
 }
 
 static void free_shard(Shard& s) {

@@ -32,7 +32,7 @@ class DistInfo(object):
 class TelescopeLikelihood(object):
 
     def __init__(self, score_matrix, opts, devices=None, dist=None, max_score=None, kernel="auto", replicas=0,
-                 smem_table_cols=-1, permute_columns=True):
+                 smem_table_cols=-1, permute_columns=False):
         """score_matrix: csr_matrix (uint16) N reads x K loci; opts: em_epsilon, max_iter, pi_prior, theta_prior.
 
         devices: list of CUDA ordinals driven from this process (default [0]).  dist: DistInfo when this process

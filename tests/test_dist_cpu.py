@@ -1,0 +1,73 @@
+"""CPU tier, world_size 2 over gloo: the sharding contract of the multi-GPU path.
+
+Reads are split into contiguous blocks; each rank computes the E-step and the per-locus M-step sums of ITS block
+only, the K-length sums are all-reduced once per iteration, and every rank then holds identical pi/theta.  That is
+exactly what libtelescope_b200 does over NCCL; here the per-rank arithmetic is the CPU oracle so the contract
+(shard boundaries, which quantities are reduced, max_score and init totals being global) is tested without GPUs.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n_rows, n_cols, out_path):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from oracle.em_numpy import EMOracle, q_lut
+    from telescope_b200.synthetic import shard_bounds, synth_csr
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_bounds(n_rows, world)[rank]
+    ip, ix, raw = synth_csr(n_rows, n_cols, 8, True, 4242, lo, hi)
+    ms = torch.tensor([int(raw.max())])
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)                       # global max score before the Q table
+    o = EMOracle(ip, ix, raw, n_cols, max_score=int(ms.item()), lut=q_lut(int(ms.item())))
+
+    def allsum(x):
+        t = torch.from_numpy(np.atleast_1d(np.asarray(x, dtype=np.float64)).copy())
+        dist.all_reduce(t)
+        return t.numpy()
+    total_wt, ambig_wt = allsum(o.total_wt)[0], allsum(o.ambig_wt)[0]
+    wmax = torch.tensor([o.weights.max()], dtype=torch.float64)
+    dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+    pisum0 = allsum(o.pisum0)
+    tpw = 200000 * wmax.item()
+    pi = theta = np.repeat(1.0 / n_cols, n_cols)
+    for _ in range(6):
+        z = o.estep(pi, theta)
+        local = np.bincount(o.indices, weights=(z * o.weights[o.row]) * o.Y[o.row], minlength=n_cols)
+        thetasum = allsum(local)                                    # the one collective per iteration
+        theta = (thetasum + tpw) / (ambig_wt + tpw * n_cols)
+        pi = (pisum0 + thetasum) / total_wt
+    np.save(out_path % rank, np.stack([pi, theta]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_em_equals_single_process(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle.em_numpy import EMOracle
+    sys.path.insert(0, ROOT)
+    from telescope_b200.synthetic import synth_csr
+    n_rows, n_cols = 30000, 400
+    port = 29500 + (os.getpid() % 2000)
+    out = str(tmp_path / "rank%d.npy")
+    mp.spawn(_worker, args=(2, port, n_rows, n_cols, out), nprocs=2, join=True)
+    a, b = np.load(out % 0), np.load(out % 1)
+    assert np.array_equal(a, b), "all ranks must hold bit-identical parameters after the all-reduce"
+    ip, ix, raw = synth_csr(n_rows, n_cols, 8, True, 4242)
+    o = EMOracle(ip, ix, raw, n_cols, em_epsilon=-1, max_iter=6).em()
+    assert np.max(np.abs(a[0] - o.pi) / np.maximum(o.pi, 1e-300)) < 1e-9
+    assert np.max(np.abs(a[1] - o.theta) / o.theta) < 1e-9
+
+
+def test_shard_bounds_cover_all_reads():
+    sys.path.insert(0, ROOT)
+    from telescope_b200.synthetic import shard_bounds
+    for n, w in [(10, 1), (10, 3), (50_000_000, 8), (7, 8)]:
+        b = shard_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))

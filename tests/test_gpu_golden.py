@@ -1,0 +1,111 @@
+"""GPU parity against golden vectors produced by the unmodified reference (tests/golden/make_golden.py), including
+the reference's published known answer for the bundled data and the CLI end to end."""
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import ROOT, Opts, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+RTOL = 1e-6
+REPORT_CALLS = [("conf", 0.9, False), ("all", 0.9, True), ("unique", 0.9, False), ("exclude", 0.9, True),
+                ("choose", 0.9, True), ("average", 0.9, True), ("exclude", 0.9, False)]
+CASES = sorted(glob.glob(os.path.join(GOLD, "case_*.npz"))) + [os.path.join(GOLD, "bundled.npz")]
+
+
+def _run(g, **kw):
+    from telescope_b200.likelihood import TelescopeLikelihood
+    m = sp.csr_matrix((g["raw"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    opts = Opts(float(g["em_epsilon"]), int(g["max_iter"]), float(g["pi_prior"]), float(g["theta_prior"]))
+    tl = TelescopeLikelihood(m, opts, **kw)
+    tl.em(use_likelihood=bool(g["use_likelihood"]))
+    return m, tl
+
+
+def _aligned(z, m):
+    z = sp.csr_matrix(z)
+    z.sort_indices()
+    K = np.int64(m.shape[1])
+    full = np.repeat(np.arange(m.shape[0], dtype=np.int64), np.diff(m.indptr)) * K + m.indices
+    sub = np.repeat(np.arange(m.shape[0], dtype=np.int64), np.diff(z.indptr)) * K + z.indices
+    out = np.zeros(m.nnz)
+    out[np.searchsorted(full, sub)] = z.data
+    return out
+
+
+@pytest.mark.parametrize("kernel", ["tiles", "rows"])
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_gpu_matches_reference_golden(path, kernel):
+    g = np.load(path)
+    m, tl = _run(g, kernel=kernel)
+    assert tl.n_iter == int(g["n_iter"])
+    assert np.array_equal(tl.Y.ravel(), g["Y"]) and np.array_equal(tl._row_info()[1], g["weights"])
+    assert rel_err(tl.diffs, g["diffs"]) < RTOL
+    assert rel_err(tl.pi, g["pi"]) < RTOL and rel_err(tl.theta, g["theta"]) < RTOL
+    assert rel_err(tl.pi_init, g["pi_init"]) < RTOL and rel_err(tl.theta_init, g["theta_init"]) < RTOL
+    assert abs(tl.lnl - float(g["lnl"])) <= RTOL * abs(float(g["lnl"]))
+    if bool(g["use_likelihood"]):
+        assert rel_err(tl.lnls, g["lnls"]) < RTOL
+    assert rel_err(_aligned(tl.z, m), g["z"]) < RTOL
+    assert rel_err(_aligned(tl.reassign("all", initial=True).astype(np.float64).multiply(tl.Q.norm(1)), m), g["z_init"]) < 1e-12
+    np.random.seed(int(g["seed"]))
+    for (meth, th, ini), ref in zip(REPORT_CALLS, g["colsums"]):
+        got = tl.reassign_colsum(meth, th, ini).astype(np.float64)
+        if meth in ("average", "conf"):
+            assert rel_err(got, ref) < RTOL, meth
+        else:
+            assert np.array_equal(got, ref), "integer counts must be bit-exact: %s initial=%s" % (meth, ini)
+    tl.close()
+
+
+def test_bundled_known_answer_and_log_lines(caplog):
+    import logging
+    g = np.load(os.path.join(GOLD, "bundled.npz"))
+    with caplog.at_level(logging.INFO):
+        from telescope_b200.likelihood import TelescopeLikelihood
+        m = sp.csr_matrix((g["raw"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+        tl = TelescopeLikelihood(m, Opts())
+        tl.em(loglev=logging.INFO)
+    msgs = [r.getMessage() for r in caplog.records]
+    assert "Final log-likelihood: 95252.596293." in msgs          # reference README.md:70-71
+    assert "EM converged after 16 iterations." in msgs
+    assert "Iteration 1, diff=1.3795" in msgs and "Iteration 16, diff=6.3301e-08" in msgs
+    tl.close()
+
+
+def _strip_version(text):
+    return re.sub(r"version:[^\t]*", "version:X", text)
+
+
+def test_cli_assign_and_resume_reproduce_reference_reports(tmp_path):
+    from telescope_b200 import cli
+    data = os.path.join(ROOT, "telescope_b200", "data")
+    out = str(tmp_path)
+    cli.main(["assign", os.path.join(data, "alignment.bam"), os.path.join(data, "annotation.gtf"), "--outdir", out, "--quiet"])
+    stats = open(os.path.join(out, "telescope-run_stats.tsv")).read()
+    counts = open(os.path.join(out, "telescope-TE_counts.tsv")).read()
+    assert _strip_version(stats) == _strip_version(open(os.path.join(GOLD, "bundled_run_stats.tsv")).read())
+    assert counts == open(os.path.join(GOLD, "bundled_TE_counts.tsv")).read()
+    assert os.path.exists(os.path.join(out, "telescope-checkpoint.npz"))
+    # resume from the checkpoint the REFERENCE wrote
+    out2 = str(tmp_path / "r")
+    os.makedirs(out2)
+    cli.main(["resume", os.path.join(GOLD, "bundled_checkpoint.npz"), "--outdir", out2, "--quiet", "--exp_tag", "again"])
+    assert open(os.path.join(out2, "again-TE_counts.tsv")).read() == counts
+    assert _strip_version(open(os.path.join(out2, "again-run_stats.tsv")).read()) == _strip_version(open(os.path.join(GOLD, "bundled_run_stats.tsv")).read())
+
+
+def test_em_can_be_called_again_and_continues():
+    g = np.load(os.path.join(GOLD, "case_cutoff.npz"))
+    m, tl = _run(g)                       # 7 iterations
+    pi7 = tl.pi.copy()
+    tl.em()                               # 7 more, continuing from the current parameters (model.py:773)
+    from oracle.em_numpy import EMOracle
+    o = EMOracle(g["indptr"], g["indices"], g["raw"], int(g["shape"][1]), float(g["em_epsilon"]), 14, 0, 200000).em()
+    assert rel_err(tl.pi, o.pi) < RTOL and not np.array_equal(tl.pi, pi7)
+    tl.close()

@@ -1,0 +1,238 @@
+"""CPU tier: host logic -- the C ABI surface, csr_matrix_plus, the BAM/GTF loader, checkpoint format, report
+writers, CLI parsing, synthetic generator.  No compute calls into the CUDA library happen here."""
+import ctypes
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import ROOT, Opts, rel_err
+from oracle.em_numpy import EMOracle
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+DATA = os.path.join(ROOT, "telescope_b200", "data")
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol():
+    from telescope_b200 import _abi
+    header = open(os.path.join(ROOT, "include", "telescope_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(tsc_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_abi.SYMBOLS), declared ^ set(_abi.SYMBOLS)
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert _abi.load().tsc_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    from telescope_b200 import _abi
+    from telescope_b200.likelihood import TelescopeLikelihood
+    if _abi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    m = sp.csr_matrix(np.array([[200, 190, 0], [0, 180, 170]], dtype=np.uint16))
+    with pytest.raises(_abi.TelescopeCudaError):
+        TelescopeLikelihood(m, Opts())
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "telescope_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), f
+
+
+# ------------------------------------------------------------------------------------------------ csr_matrix_plus
+def test_csr_matrix_plus_known_answers():
+    """reference tests/test_sparse_plus.py:24-66 and the docstrings of sparse_plus.py:33-41,76-85,106-115."""
+    from telescope_b200.sparse_plus import csr_matrix_plus as C
+    m = C(np.array([[1, 0, 2], [0, 0, 3], [4, 5, 6]]))
+    assert np.allclose(m.norm().toarray(), np.array([[1, 0, 2], [0, 0, 3], [4, 5, 6]]) / 21.0)
+    assert np.allclose(m.norm(1).toarray(), [[1 / 3., 0, 2 / 3.], [0, 0, 1], [4 / 15., 5 / 15., 6 / 15.]])
+    z = C(np.array([[1, 0, 2], [0, 0, 0], [4, 5, 6]]))
+    assert np.allclose(z.norm(1).toarray(), [[1 / 3., 0, 2 / 3.], [0, 0, 0], [4 / 15., 5 / 15., 6 / 15.]])   # zero row stays zero
+    s = C([[10, 0, 20], [0, 0, 30], [40, 50, 60]])
+    assert np.allclose(s.scale().toarray(), [[1 / 6., 0, 2 / 6.], [0, 0, 0.5], [4 / 6., 5 / 6., 1]])
+    assert np.allclose(s.scale(1).toarray(), [[0.5, 0, 1], [0, 0, 1], [4 / 6., 5 / 6., 1]])
+    b = C([[6, 0, 2], [0, 0, 3], [4, 5, 6]])
+    assert np.array_equal(b.binmax(1).toarray(), [[1, 0, 0], [0, 0, 1], [0, 0, 1]])
+    assert np.array_equal(b.count(1).ravel(), [2, 1, 3])
+    assert isinstance(m.norm(1), C)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        m.save(os.path.join(d, "m"))
+        assert m.check_equal(C.load(os.path.join(d, "m.npz")))
+
+
+def test_choose_random_consumes_rng_like_reference_loop():
+    from telescope_b200.sparse_plus import csr_matrix_plus as C
+    from telescope_b200.sparse_plus import draw_picks
+    counts = np.random.default_rng(0).integers(2, 40, size=500)
+    np.random.seed(123)
+    seq = np.array([np.random.choice(range(5, 5 + n)) - 5 for n in counts])      # sparse_plus.py:149
+    np.random.seed(123)
+    assert np.array_equal(draw_picks(counts), seq)
+    rng = np.random.default_rng(1)
+    d = (rng.random((200, 30)) < 0.2).astype(np.int8)
+    m = C(d)
+    np.random.seed(7)
+    mine = m.choose_random(1)
+    np.random.seed(7)
+    ref = m.copy()
+    for a, b in zip(ref.indptr[:-1], ref.indptr[1:]):                                # the reference's loop, verbatim semantics
+        if b - a > 1:
+            ch = np.random.choice(range(a, b))
+            ref.data[a:ch] = 0
+            ref.data[ch + 1:b] = 0
+    ref.eliminate_zeros()
+    assert (mine != ref).nnz == 0
+
+
+# ------------------------------------------------------------------------------------------------ loader / checkpoint
+class AssignOpts(Opts):
+    samfile = os.path.join(DATA, "alignment.bam")
+    gtffile = os.path.join(DATA, "annotation.gtf")
+    no_feature_key, overlap_threshold, overlap_mode, stranded_mode, ncpu = "__no_feature", 0.2, "threshold", "None", 1
+    version = "GOLDEN"
+    updated_sam = False
+
+
+@pytest.fixture(scope="module")
+def bundled_ts():
+    from telescope_b200.host.annotation import Annotation
+    from telescope_b200.host.telescope import Telescope
+    opts = AssignOpts()
+    ts = Telescope(opts)
+    ts.load_alignment(Annotation(opts.gtffile, "locus", "None"))
+    return ts
+
+
+def test_loader_reproduces_bundled_matrix(bundled_ts):
+    g = np.load(os.path.join(GOLD, "bundled.npz"))
+    ts = bundled_ts
+    assert ts.shape == (1000, 59) and ts.raw_scores.nnz == 18471
+    assert ts.raw_scores.dtype == np.uint16 and ts.raw_scores.indices.dtype == np.int32
+    assert np.array_equal(ts.raw_scores.data, g["raw"]) and np.array_equal(ts.raw_scores.indices, g["indices"])
+    assert np.array_equal(ts.raw_scores.indptr, g["indptr"])
+    # run info of the bundled report (telescope/data/telescope_report.tsv:1)
+    want = dict(annotated_features=99, total_fragments=1000, pair_mapped=1000, pair_mixed=0, single_mapped=0, unmapped=0,
+                unique=0, ambig=1000, overlap_unique=0, overlap_ambig=1000)
+    for k, v in want.items():
+        assert ts.run_info[k] == v, k
+    assert ts.get_random_seed() == 0
+    assert sorted(ts.feat_index, key=ts.feat_index.get)[0] == "__no_feature"
+
+
+def test_checkpoint_is_the_reference_format(bundled_ts, tmp_path):
+    from telescope_b200.host.telescope import Telescope
+    p = str(tmp_path / "ckpt")
+    bundled_ts.save(p)
+    mine, ref = np.load(p + ".npz"), np.load(os.path.join(GOLD, "bundled_checkpoint.npz"))   # written by the reference's save()
+    assert sorted(mine.files) == sorted(ref.files)
+    for k in ref.files:
+        assert mine[k].dtype.kind == ref[k].dtype.kind and mine[k].shape == ref[k].shape, k
+        if k != "_run_info":
+            assert np.array_equal(mine[k], ref[k]), k
+    back = Telescope.load(os.path.join(GOLD, "bundled_checkpoint.npz"))                      # and we read the reference's file
+    assert back.shape == (1000, 59) and back.run_info["total_fragments"] == 1000
+    assert (back.raw_scores != bundled_ts.raw_scores).nnz == 0
+    assert back.get_random_seed() == 0
+
+
+def test_mapping_to_matrix_keeps_max_and_drops_unannotated_reads():
+    from telescope_b200.host.telescope import Telescope
+    from collections import Counter
+    ts = Telescope.__new__(Telescope)
+    ts.opts = AssignOpts()
+    ts.read_index, ts.feat_index = {}, {}
+    info = Counter()
+    reads = ["r1", "r1", "r1", "r2", "r3", "r3"]
+    feats = ["A", "B", "A", "__no_feature", "B", "__no_feature"]
+    ts._mapping_to_matrix(reads, feats, [10, 12, 11, 9, 10, 10], [100, 100, 100, 100, 90, 90], (9, 12), info)
+    # rescale = score - min + 1, value = rescale + length; duplicates keep the max; r2 hits no feature -> dropped
+    assert ts.shape == (2, 3) and ts.read_index == {"r1": 0, "r3": 1}
+    assert np.array_equal(ts.raw_scores.toarray(), [[0, 103, 104], [92, 0, 92]])
+    assert info["overlap_unique"] == 0 and info["overlap_ambig"] == 2
+
+
+# ------------------------------------------------------------------------------------------------ reports
+class OracleModel(object):
+    """Stands in for the GPU class in CPU-tier report tests: same reassign_colsum / pi / pi_init surface."""
+
+    def __init__(self, m, opts):
+        self.o = EMOracle(m.indptr, m.indices, m.data, m.shape[1], opts.em_epsilon, opts.max_iter, opts.pi_prior, opts.theta_prior).em()
+        self.pi, self.pi_init = self.o.pi, self.o.pi_init
+
+    def reassign_colsum(self, method, thresh=0.9, initial=False):
+        return self.o.reassign_colsum(method, thresh, initial)
+
+
+def strip_version(text):
+    return re.sub(r"version:[^\t]*", "version:X", text)
+
+
+def test_output_report_matches_reference_files(bundled_ts, tmp_path):
+    ts = bundled_ts
+    ts.opts = AssignOpts()
+    np.random.seed(ts.get_random_seed())
+    ts.output_report(OracleModel(ts.raw_scores, ts.opts), str(tmp_path / "s.tsv"), str(tmp_path / "c.tsv"))
+    assert strip_version(open(tmp_path / "s.tsv").read()) == strip_version(open(os.path.join(GOLD, "bundled_run_stats.tsv")).read())
+    assert open(tmp_path / "c.tsv").read() == open(os.path.join(GOLD, "bundled_TE_counts.tsv")).read()
+    head = open(tmp_path / "s.tsv").readline()
+    assert head.startswith("## RunInfo\tversion:") and "overlap_ambig:1000transcript\t" in head   # glued header, model.py:471
+
+
+# ------------------------------------------------------------------------------------------------ CLI / misc
+def test_cli_options_and_defaults():
+    from telescope_b200 import cli
+    import argparse
+    p = argparse.ArgumentParser()
+    cli.add_assign_arguments(p)
+    a = p.parse_args(["x.bam", "y.gtf"])
+    assert (a.pi_prior, a.theta_prior, a.em_epsilon, a.max_iter, a.reassign_mode, a.conf_prob) == (0, 200000, 1e-7, 100, "exclude", 0.9)
+    assert a.overlap_threshold == 0.2 and a.no_feature_key == "__no_feature" and a.attribute == "locus" and not a.skip_em
+    p = argparse.ArgumentParser()
+    cli.add_resume_arguments(p)
+    r = p.parse_args(["ckpt.npz", "--max_iter", "5", "--use_likelihood", "--devices", "0,1"])
+    o = cli.Options(r)
+    assert o.max_iter == 5 and o.use_likelihood and o.device_list() == [0, 1]
+    assert o.outfile_path("run_stats.tsv") == os.path.join(".", "telescope-run_stats.tsv")
+    buf = io.StringIO()
+    import contextlib
+    with contextlib.redirect_stdout(buf):
+        cli.main(["test"])
+    assert buf.getvalue().startswith("telescope assign ") and buf.getvalue().strip().endswith("annotation.gtf")
+
+
+def test_synthetic_generator_is_canonical_and_shardable():
+    from telescope_b200.synthetic import shard_bounds, synth_csr
+    N, K = 2_200_000, 4000
+    ip, ix, raw = synth_csr(N, K, 10, False, 9)
+    lens = np.diff(ip)
+    assert 9.5 < lens.mean() < 10.5 and 0.19 < np.mean(lens == 1) < 0.21
+    inner = np.ones(ix.size, bool)
+    inner[ip[:-1]] = False
+    assert (np.diff(ix.astype(np.int64))[inner[1:]] > 0).all(), "strictly increasing loci inside a read"
+    assert ix.min() >= 0 and ix.max() < K and raw.min() >= 140 and raw.max() <= 211
+    parts = [synth_csr(N, K, 10, False, 9, lo, hi) for lo, hi in shard_bounds(N, 3)]
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), ix) and np.array_equal(np.concatenate([p[2] for p in parts]), raw)
+    ipz, _, _ = synth_csr(50000, 3000, 20, True, 9)
+    assert np.diff(ipz).max() == 200
+
+
+def test_bam_reader_basics():
+    from telescope_b200.host import bam
+    with bam.AlignmentReader(os.path.join(DATA, "alignment.bam")) as sf:
+        assert len(sf.references) > 0
+        n, names, first = 0, set(), None
+        for seg in sf:
+            first = first or seg
+            n += 1
+            names.add(seg.name)
+    assert n == 66414 and len(names) == 1000
+    assert first.is_paired and first.is_proper_pair and first.score is not None and first.blocks

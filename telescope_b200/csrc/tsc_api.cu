@@ -113,6 +113,7 @@ struct Shard {
     double *pi_init = nullptr, *theta_init = nullptr, *pisum0 = nullptr, *acc = nullptr, *thetasum = nullptr;
     double *ones = nullptr, *tmp_a = nullptr, *tmp_b = nullptr, *tmp_c = nullptr, *colsum = nullptr;
     int* perm = nullptr;      // original -> internal locus index (nullptr = identity)
+    int* rep = nullptr;       // internal locus -> representative of its class of identical columns (nullptr = none)
     Consts* consts = nullptr;
     EmState* st = nullptr;
     EmState* st_host = nullptr;    // pinned, 2 slots
@@ -140,6 +141,7 @@ struct tsc_handle {
     long long n_rows_user = 0, n_rows = 0, nnz = 0;
     std::vector<long long> rowmap;        // compacted read -> caller's read index (empty when no empty reads)
     std::vector<int> perm, inv;           // perm[original] = internal; inv[internal] = original
+    int n_dup_loci = 0;                   // loci whose column duplicates an earlier locus's
     Consts consts{};
     std::vector<double> pisum0_host;
     bool em_done = false;
@@ -293,7 +295,7 @@ static void free_shard(Shard& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     void* ptrs[] = {s.indptr, s.col, s.q, s.wy, s.tiles, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
                     s.pi_init, s.theta_init, s.pisum0, s.acc, s.thetasum, s.ones, s.tmp_a, s.tmp_b, s.tmp_c, s.colsum,
-                    s.perm, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad};
+                    s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.st_host) cudaFreeHost(s.st_host);
     for (auto& e : s.ev_poll) if (e) cudaEventDestroy(e);
@@ -434,11 +436,11 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         CU(cudaMalloc(&s.wy, sizeof(double) * std::max<long long>(s.n_rows, 1)));
         CU(cudaMalloc(&raw_d[i], sizeof(uint16_t) * std::max<long long>(s.nnz, 1)));
         CU(cudaMalloc(&colin_d[i], sizeof(int) * std::max<long long>(s.nnz, 1)));
-        CU(cudaMalloc(&cnt_d[i], sizeof(unsigned long long) * K));
+        CU(cudaMalloc(&cnt_d[i], sizeof(unsigned long long) * K * 3));
         CU(cudaMalloc(&lut_d[i], sizeof(double) * lut_len));
         CU(cudaMalloc(&s.bad, sizeof(int)));
         CU(cudaMemsetAsync(s.bad, 0, sizeof(int), s.stream));
-        CU(cudaMemsetAsync(cnt_d[i], 0, sizeof(unsigned long long) * K, s.stream));
+        CU(cudaMemsetAsync(cnt_d[i], 0, sizeof(unsigned long long) * K * 3, s.stream));
         CU(cudaMemsetAsync(s.col + s.nnz, 0, sizeof(int) * pad, s.stream));
         CU(cudaMemsetAsync(s.q + s.nnz, 0, sizeof(double) * pad, s.stream));
         // local read pointers rebased to the shard
@@ -450,7 +452,8 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         CU(cudaMemcpyAsync(lut_d[i], q_lut, sizeof(double) * lut_len, cudaMemcpyHostToDevice, s.stream));
         h->h2d += sizeof(long long) * (s.n_rows + 1) + (sizeof(uint16_t) + sizeof(int)) * s.nnz + sizeof(double) * lut_len;
         CU(cudaStreamSynchronize(s.stream));   // lip goes out of scope
-        k_col_hist<<<grid_for(s.nnz, 256, s.n_sm * 16), 256, 0, s.stream>>>(colin_d[i], s.nnz, K, cnt_d[i], s.bad);
+        k_col_signature<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(
+            s.indptr, s.n_rows, colin_d[i], raw_d[i], K, ((unsigned long long)s.world_rank << 40), cnt_d[i], s.bad);
         LAUNCH(h);
         CU(cudaGetLastError());
         // tiles for the fused kernel
@@ -468,7 +471,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
             NC(g_nccl.GroupStart());
             for (int i = 0; i < n_local; ++i) {
                 CU(cudaSetDevice(h->shards[i].dev));
-                NC(g_nccl.AllReduce(cnt_d[i], cnt_d[i], K, ncclUint64, ncclSum, h->shards[i].comm, h->shards[i].stream));
+                NC(g_nccl.AllReduce(cnt_d[i], cnt_d[i], (size_t)K * 3, ncclUint64, ncclSum, h->shards[i].comm, h->shards[i].stream));
             }
             NC(g_nccl.GroupEnd());
         }
@@ -479,18 +482,48 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
             CU(cudaStreamSynchronize(s.stream));
             if (bad) return fail(TSC_ERR_ARG, "column index out of range [0, n_cols)");
         }
-        std::vector<unsigned long long> cnt(K);
+        std::vector<unsigned long long> cnt((size_t)K * 3);
         Shard& s0 = h->shards[0];
         CU(cudaSetDevice(s0.dev));
-        CU(cudaMemcpyAsync(cnt.data(), cnt_d[0], sizeof(unsigned long long) * K, cudaMemcpyDeviceToHost, s0.stream));
+        CU(cudaMemcpyAsync(cnt.data(), cnt_d[0], sizeof(unsigned long long) * K * 3, cudaMemcpyDeviceToHost, s0.stream));
         CU(cudaStreamSynchronize(s0.stream));
-        h->d2h += sizeof(unsigned long long) * K;
+        h->d2h += sizeof(unsigned long long) * K * 3;
         h->inv.resize(K);
         std::iota(h->inv.begin(), h->inv.end(), 0);
         if (cfg.permute_columns)
             std::stable_sort(h->inv.begin(), h->inv.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
         h->perm.resize(K);
         for (int i = 0; i < K; ++i) h->perm[h->inv[i]] = i;
+        // classes of identical columns (same count and both signatures); empty loci are trivially identical too
+        std::vector<int> order(K);
+        std::iota(order.begin(), order.end(), 0);
+        auto key_less = [&](int a, int b) {
+            if (cnt[a] != cnt[b]) return cnt[a] < cnt[b];
+            if (cnt[K + a] != cnt[K + b]) return cnt[K + a] < cnt[K + b];
+            if (cnt[2 * (size_t)K + a] != cnt[2 * (size_t)K + b]) return cnt[2 * (size_t)K + a] < cnt[2 * (size_t)K + b];
+            return a < b;
+        };
+        auto key_eq = [&](int a, int b) {
+            return cnt[a] == cnt[b] && cnt[K + a] == cnt[K + b] && cnt[2 * (size_t)K + a] == cnt[2 * (size_t)K + b];
+        };
+        std::sort(order.begin(), order.end(), key_less);
+        std::vector<int> rep_internal(K);
+        h->n_dup_loci = 0;
+        for (int i = 0; i < K;) {
+            int j = i;
+            while (j < K && key_eq(order[i], order[j])) ++j;
+            for (int t = i; t < j; ++t) rep_internal[h->perm[order[t]]] = h->perm[order[i]];   // order[i] = smallest original index
+            h->n_dup_loci += (j - i - 1);
+            i = j;
+        }
+        if (h->n_dup_loci > 0) {
+            for (auto& s : h->shards) {
+                CU(cudaSetDevice(s.dev));
+                CU(cudaMalloc(&s.rep, sizeof(int) * K));
+                CU(cudaMemcpyAsync(s.rep, rep_internal.data(), sizeof(int) * K, cudaMemcpyHostToDevice, s.stream));
+                CU(cudaStreamSynchronize(s.stream));
+            }
+        }
     }
     const size_t kb = sizeof(double) * K;
     for (int i = 0; i < n_local; ++i) {
@@ -797,7 +830,7 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
         for (auto& s : h->shards) {
             CU(cudaSetDevice(s.dev));
             UpdateArgs a{s.thetasum, s.pisum0, s.consts, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
-                         s.pi_init, s.theta_init, s.st, s.diffs, K, T, use_likelihood ? 1 : 0, eps};
+                         s.pi_init, s.theta_init, s.st, s.diffs, K, T, use_likelihood ? 1 : 0, eps, s.rep};
             k_update<<<1, 1024, 0, s.stream>>>(a);
             LAUNCH(h);
             CU(cudaGetLastError());
@@ -923,10 +956,10 @@ extern "C" int tsc_get_z(tsc_handle* h, int32_t initial, double* z_data) {
 }
 
 __global__ void k_mstep_tail(const double* __restrict__ thetasum, const double* __restrict__ pisum0, const Consts* __restrict__ c,
-                             double* __restrict__ pi_hat, double* __restrict__ theta_hat, int K) {
+                             double* __restrict__ pi_hat, double* __restrict__ theta_hat, int K, const int* __restrict__ rep) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= K) return;
-    const double ts = thetasum[j];
+    const double ts = thetasum[rep ? rep[j] : j];
     theta_hat[j] = (ts + c->theta_prior_wt) / c->theta_denom;
     const double pisum = pisum0[j] + ts;
     pi_hat[j] = (pisum + c->pi_prior_wt) / c->pi_denom;
@@ -957,7 +990,7 @@ extern "C" int tsc_mstep(tsc_handle* h, const double* z_data, double* pi_hat, do
     ALLREDUCE(h, s.tmp_c, (size_t)K, ncclFloat64, ncclSum);
     Shard& s = h->shards[0];
     CU(cudaSetDevice(s.dev));
-    k_mstep_tail<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.tmp_c, s.pisum0, s.consts, s.tmp_a, s.tmp_b, K);
+    k_mstep_tail<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.tmp_c, s.pisum0, s.consts, s.tmp_a, s.tmp_b, K, s.rep);
     LAUNCH(h);
     CU(cudaGetLastError());
     int rc = sync_all(h);

@@ -116,14 +116,31 @@ __global__ void k_build_q(const uint16_t* __restrict__ raw, const int* __restric
     }
 }
 
-__global__ void k_col_hist(const int* __restrict__ col, long long nnz, int n_cols,
-                           unsigned long long* __restrict__ cnt, int* __restrict__ bad) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {   // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+    x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+    x ^= x >> 31;
+    return x;
+}
+
+// Per-locus entry count and an order-independent signature of the locus's column {(read, score)}: two 64-bit sums of
+// independent hashes.  Loci with equal (count, sig1, sig2) hold identical columns; the reference gives such loci
+// bit-identical pi/theta (its column sums run in read order), which reassign()'s exact tie test depends on.
+__global__ void k_col_signature(const long long* __restrict__ indptr, long long n_rows, const int* __restrict__ col,
+                                const uint16_t* __restrict__ raw, int n_cols, unsigned long long row_key0,
+                                unsigned long long* __restrict__ sig /* 3*K: count, sum h1, sum h2 */, int* __restrict__ bad) {
+    long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < nnz; i += stride) {
-        const int c = col[i];
-        if (c < 0 || c >= n_cols) { *bad = 1; continue; }
-        atomicAdd(cnt + c, 1ULL);
+    for (; r < n_rows; r += stride) {
+        const unsigned long long rk = mix64(row_key0 + (unsigned long long)r);
+        for (long long k = indptr[r]; k < indptr[r + 1]; ++k) {
+            const int c = col[k];
+            if (c < 0 || c >= n_cols) { *bad = 1; continue; }
+            const unsigned long long e = rk ^ ((unsigned long long)raw[k] * 0x9e3779b97f4a7c15ULL);
+            atomicAdd(sig + c, 1ULL);
+            atomicAdd(sig + n_cols + c, mix64(e));
+            atomicAdd(sig + 2 * (size_t)n_cols + c, mix64(e ^ 0xd6e8feb86659fd93ULL));
+        }
     }
 }
 
@@ -199,6 +216,7 @@ struct UpdateArgs {
     double* diffs;
     int K, max_iter, use_lnl;
     double eps;
+    const int* rep;           // rep[j] = first locus whose column is identical to j's (nullptr: all distinct)
 };
 
 // mstep tail (model.py:734-742), diff_est (model.py:781) and the loop control of model.py:788-796.  One block:
@@ -211,7 +229,7 @@ __global__ void __launch_bounds__(1024) k_update(UpdateArgs a) {
     const Consts c = *a.c;
     double local = 0;
     for (int j = threadIdx.x; j < a.K; j += blockDim.x) {
-        const double ts = a.thetasum[j];
+        const double ts = a.thetasum[a.rep ? a.rep[j] : j];    // identical loci share one sum -> exact ties survive
         const double th = (ts + c.theta_prior_wt) / c.theta_denom;
         const double pisum = a.pisum0[j] + ts;
         const double pn = (pisum + c.pi_prior_wt) / c.pi_denom;

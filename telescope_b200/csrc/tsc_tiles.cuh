@@ -38,7 +38,9 @@ static_assert(sizeof(Tile) == 32, "tile descriptor is one 32-byte sector");
 
 constexpr int kTileWarps = 16;                 // warps per block of the tile kernel
 constexpr int kTileThreads = kTileWarps * 32;
-constexpr int kScratch = 132;                  // doubles of per-warp scratch (128 reads + slack)
+constexpr int kScrN = 128;                     // per-warp scratch: the tile's numerators (layout transposition)
+constexpr int kScrG = 132;                     //                   per-read totals, then per-read scale g
+constexpr int kScratch = kScrN + kScrG;        // doubles per warp
 
 template <bool SMEM_TAB>
 __device__ __forceinline__ double gather_pt(const double* __restrict__ pt, const double* s_tab, int s_cols, int c) {
@@ -57,6 +59,10 @@ __device__ __forceinline__ int ld_stream(const int* p) {
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+// v += y when a >= b (predicated add: one DADD instead of two selects and an add)
+__device__ __forceinline__ void add_if_ge(double& v, double y, int a, int b) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, %3;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(v) : "d"(y), "r"(a), "r"(b));
+}
 
 template <bool SMEM_TAB>
 __global__ void __launch_bounds__(kTileThreads)
@@ -65,7 +71,8 @@ k_fused_tiles(const Tile* __restrict__ tiles, long long n_tiles, const double* _
               int s_cols, const EmState* __restrict__ st) {
     extern __shared__ double s_dyn[];
     if (st->done) return;
-    double* s_scr = s_dyn + (threadIdx.x >> 5) * kScratch;       // per-warp scratch
+    double* s_n = s_dyn + (threadIdx.x >> 5) * kScratch;         // per-warp scratch
+    double* s_g = s_n + kScrN;
     const double* s_tab = s_dyn + kTileWarps * kScratch;          // optional copy of pt[0 .. s_cols)
     if (SMEM_TAB) {
         double* t = s_dyn + kTileWarps * kScratch;
@@ -75,19 +82,26 @@ k_fused_tiles(const Tile* __restrict__ tiles, long long n_tiles, const double* _
     double* my = acc + (size_t)(blockIdx.x % R) * K;
     const int lane = threadIdx.x & 31;
     const unsigned le_mask = 0xffffffffu >> (31 - lane);          // lanes <= mine
+    const int wsel = lane >> 3, sh = (lane & 7) * 4;              // blocked layout: my 4 flag bits live in F[wsel] >> sh
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;
 
+    int4 d0 = __ldg(reinterpret_cast<const int4*>(tiles + t));
+    uint4 fl = __ldg(reinterpret_cast<const uint4*>(tiles + t) + 1);
     for (; t < n_tiles; t += nwarps) {
-        const int4 d0 = __ldg(reinterpret_cast<const int4*>(tiles + t));
-        const uint4 fl = __ldg(reinterpret_cast<const uint4*>(tiles + t) + 1);
         const long long base = ((long long)(unsigned)d0.x) | ((long long)d0.y << 32);
         const int row0 = d0.z;
         const int end = d0.w & 0xff, nrows = (d0.w >> 16) & 0xff;
+        const unsigned F[4] = {fl.x, fl.y, fl.z, fl.w};
+        // next tile's descriptor: in flight while this tile is processed
+        const long long tn = (t + nwarps < n_tiles) ? t + nwarps : t;
+        d0 = __ldg(reinterpret_cast<const int4*>(tiles + tn));
+        fl = __ldg(reinterpret_cast<const uint4*>(tiles + tn) + 1);
 
         if (end == 0) {
             // ---- long read: the whole warp walks it twice
-            const long long len = ((long long)fl.x) | ((long long)fl.y << 32);
+            const long long len = ((long long)F[0]) | ((long long)F[1] << 32);
             const long long hi = base + len;
             double sum = 0;
             for (long long p = base + lane; p < hi; p += 32)
@@ -104,63 +118,71 @@ k_fused_tiles(const Tile* __restrict__ tiles, long long n_tiles, const double* _
             continue;
         }
 
-        // ---- regular tile: 4 rounds of 32 consecutive entries
-        const unsigned F[4] = {fl.x, fl.y, fl.z, fl.w};
+        // ---- regular tile.  Lane-consecutive layout: lane l owns entries 32e + l
+        const int* colp = col + base + lane;
+        const double* qp = q + base + lane;
         int cc[4];
         double qq[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {      // all 8 loads in flight before anything is consumed (entries past the
-            cc[e] = ld_stream(col + base + 32 * e + lane);   // tile are padding or the next tile's: harmless)
-            qq[e] = ld_stream(q + base + 32 * e + lane);
+        for (int e = 0; e < 4; ++e) {      // 8 loads in flight before anything is consumed (entries past the tile
+            cc[e] = ld_stream(colp + 32 * e);                    // are padding or the next tile's: harmless)
+            qq[e] = ld_stream(qp + 32 * e);
         }
+        // w*Y of my read (row phase below), requested early
+        const double w_mine = (lane < nrows) ? __ldg(wy + row0 + lane) : 0.0;
         double n[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const bool valid = (32 * e + lane) < end;
-            n[e] = valid ? qq[e] * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, cc[e]) : 0.0;
+            n[e] = ((32 * e + lane) < end) ? qq[e] * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, cc[e]) : 0.0;
+            s_n[32 * e + lane] = n[e];
         }
-        // independent segmented inclusive scans of the four rounds
-        double x[4];
-        int lr[4];
-        int below = 0;                     // read starts before the current round
+        __syncwarp();
+        // Blocked layout for the row sums: lane l sums entries 4l .. 4l+3, one segmented scan over the 32 lane tails
+        const double2 ma = *reinterpret_cast<const double2*>(s_n + 4 * lane);
+        const double2 mb = *reinterpret_cast<const double2*>(s_n + 4 * lane + 2);
+        const double m[4] = {ma.x, ma.y, mb.x, mb.y};
+        const unsigned w_lo = F[wsel];
+        const unsigned w_hi = (wsel < 3) ? F[(wsel + 1) & 3] : 1u;          // position 128 counts as a read start
+        const unsigned five = __funnelshift_r(w_lo, w_hi, sh) & 0x1fu;     // my 4 entries + the one after
+        const int pc0 = __popc(F[0]), pc1 = pc0 + __popc(F[1]), pc2 = pc1 + __popc(F[2]);
+        const int below = (wsel == 0 ? 0 : wsel == 1 ? pc0 : wsel == 2 ? pc1 : pc2) + __popc(w_lo & ((1u << sh) - 1u));
+        double tail = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { if ((five >> e) & 1u) tail = 0; tail += m[e]; }
+        const unsigned heads = __ballot_sync(0xffffffffu, (five & 0xfu) != 0u);
+        const unsigned hle = heads & le_mask;
+        const int headlane = hle ? (31 - __clz(hle)) : 0;
+        double x = tail;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, x, d);
+            add_if_ge(x, y, lane - d, headlane);
+        }
+        double run = __shfl_up_sync(0xffffffffu, x, 1);
+        if (lane == 0) run = 0.0;
+        // an entry followed by a read start (or the tile end) closes its read: publish that read's total
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const unsigned hl = F[e] & le_mask;
-            const int headlane = hl ? (31 - __clz(hl)) : 0;
-            double v = n[e];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const double y = __shfl_up_sync(0xffffffffu, v, d);
-                if (lane - d >= headlane) v += y;
-            }
-            x[e] = v;
-            lr[e] = below + __popc(hl) - 1;
-            below += __popc(F[e]);
-        }
-        // carry the open read's partial sum from round to round and publish read totals
-        double carry = 0.0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if ((F[e] & le_mask) == 0u) x[e] += carry;            // still inside the read that was open at round start
-            // an entry closes its read when the next entry starts one (position 128 counts as a start)
-            const unsigned nxt = (e < 3) ? F[e + 1] : 1u;
-            const unsigned closes = (F[e] >> 1) | (nxt << 31);
-            const bool last = (closes >> lane) & 1u;
-            if (last && (32 * e + lane) < end) s_scr[lr[e]] = x[e];
-            const double x31 = __shfl_sync(0xffffffffu, x[e], 31);
-            carry = (closes >> 31) ? 0.0 : x31;
+            if ((five >> e) & 1u) run = 0.0;
+            run += m[e];
+            if (((five >> (e + 1)) & 1u) && (4 * lane + e) < end) s_g[below + __popc(five & ((2u << e) - 1u)) - 1] = run;
         }
         __syncwarp();
         // one lane per read: g = (w*Y) * recip0(total)
-        for (int rho = lane; rho < nrows; rho += 32) {
+        if (lane < nrows) s_g[lane] = (w_mine != 0.0) ? w_mine * recip0(s_g[lane]) : 0.0;
+        for (int rho = lane + 32; rho < nrows; rho += 32) {
             const double w = wy[row0 + rho];
-            s_scr[rho] = (w != 0.0) ? w * recip0(s_scr[rho]) : 0.0;
+            s_g[rho] = (w != 0.0) ? w * recip0(s_g[rho]) : 0.0;
         }
         __syncwarp();
+        // back in the lane-consecutive layout: neighbouring lanes hit neighbouring loci, the REDs coalesce per sector
+        int nb = 0;                        // read starts before the current round
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+            const int lr = nb + __popc(F[e] & le_mask) - 1;
+            nb += __popc(F[e]);
             if ((32 * e + lane) < end) {
-                const double c = n[e] * s_scr[lr[e]];
+                const double c = n[e] * s_g[lr];
                 if (c != 0.0) atomicAdd(my + cc[e], c);
             }
         }

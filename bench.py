@@ -307,6 +307,14 @@ def main():
     kms = tl.kernel_times_ms()
     kern_ms = max_over_ranks(float(np.mean(kms)) if len(kms) else float("nan"))
 
+    # other device passes of the path, timed alone (no host copies): standalone E-step (writes z), log-likelihood,
+    # one reassign mode
+    passes = {}
+    for name in ("estep", "lnl", "reassign"):
+        try:
+            passes[name] = max_over_ranks(tl.time_pass(name, 3))
+        except Exception as exc:      # e.g. not enough memory for the 8 B/entry z buffer
+            passes[name] = None
     value = K / (dev_ms * 1e-3)
     peak, peak_src = hbm_peak()
     rows_local = hi - lo
@@ -341,6 +349,14 @@ def main():
                 "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
             },
             "final_lnl": tl.lnl,
+            "other_kernels": {
+                "estep_z": None if not passes.get("estep") else {
+                    "ms": passes["estep"], "algorithmic_bytes": local_nnz * 20.0 + (rows_local + 1) * 4.0,
+                    "achieved_gbs": (local_nnz * 20.0 + (rows_local + 1) * 4.0) / (passes["estep"] * 1e-3) / 1e9,
+                    "frac": (local_nnz * 20.0 + (rows_local + 1) * 4.0) / (passes["estep"] * 1e-3) / 1e9 / peak,
+                    "what": "k_tiles<TILE_Z>: E-step alone, reads Q+locus, writes z (nnz*20 + (N+1)*4 bytes, SURVEY 8d)"},
+                "lnl_ms": passes.get("lnl"), "reassign_exclude_ms": passes.get("reassign"),
+            },
         }
 
     # ---- CPU arm beside it (rank 0, single-GPU run only) + parity of the GPU path on the same sample

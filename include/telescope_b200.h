@@ -121,6 +121,13 @@ int tsc_get_kernel_times(tsc_handle* h, float* ms_out, int32_t max_n, int32_t* n
 /* device time (ms, CUDA events on the library's stream of local shard 0) of the whole last tsc_em loop, first
  * kernel to the final log-likelihood reduction */
 int tsc_get_em_device_ms(tsc_handle* h, float* ms_out);
+/*
+ * Diagnostic: run one device pass `reps` times on local shard 0 without any host copy and return the mean device
+ * time (CUDA events).  pass_id: 0 = fused E+M kernel (accumulators are discarded), 1 = E-step alone writing z
+ * (model.py:702-722), 2 = log-likelihood pass (model.py:744-760), 3 = reassign column sums, mode exclude.
+ * Does not change pi/theta or the EM state.
+ */
+int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float* mean_ms);
 /* launches = kernels this library launched since creation; bytes moved over PCIe by this handle */
 int tsc_get_counters(tsc_handle* h, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
 

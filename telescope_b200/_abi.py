@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtelescope_b200.so")
+LIB_PATH = os.environ.get("TELESCOPE_B200_LIB") or os.path.join(_HERE, "libtelescope_b200.so")
 
 TSC_OK, TSC_ERR_ARG, TSC_ERR_CUDA, TSC_ERR_NCCL, TSC_ERR_STATE, TSC_ERR_ALLOC = range(6)
 METHODS = {"exclude": 0, "choose": 1, "average": 2, "conf": 3, "unique": 4, "all": 5}
@@ -22,7 +22,7 @@ SYMBOLS = (
     "tsc_config_default", "tsc_create", "tsc_destroy", "tsc_get_constants", "tsc_get_row_info", "tsc_get_q",
     "tsc_em", "tsc_get_kernel_times", "tsc_get_counters", "tsc_get_params", "tsc_set_params", "tsc_estep",
     "tsc_mstep", "tsc_calculate_lnl", "tsc_get_z", "tsc_reassign_nbest", "tsc_reassign_colsum",
-    "tsc_reassign_data", "tsc_get_em_device_ms", "tsc_pinned_alloc", "tsc_pinned_free",
+    "tsc_reassign_data", "tsc_get_em_device_ms", "tsc_pinned_alloc", "tsc_pinned_free", "tsc_time_pass",
 )
 
 
@@ -86,6 +86,7 @@ def load():
     lib.tsc_pinned_alloc.restype = C.c_void_p
     lib.tsc_pinned_free.argtypes = [vp]
     lib.tsc_pinned_free.restype = None
+    lib.tsc_time_pass.argtypes = [vp, i32, i32, C.POINTER(C.c_float)]
     lib.tsc_get_counters.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.tsc_get_params.argtypes = [vp, dp, dp, dp, dp]
     lib.tsc_set_params.argtypes = [vp, dp, dp]

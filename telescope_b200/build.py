@@ -35,19 +35,21 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
 
 
-def build_library(force=False, verbose=False):
-    """Compile the CUDA library; returns its path.  Raises on failure -- there is no fallback."""
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, out=None, defines=()):
+    """Compile the CUDA library; returns its path.  Raises on failure -- there is no fallback.
+    `out` / `defines` build tuning variants (e.g. -DTSC_TILE_WARPS=8) next to the default library."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB] + SOURCES + ["-ldl"]
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out or LIB] + SOURCES + ["-ldl"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed (exit %d)" % res.returncode)
-    with open(os.path.join(HERE, "libtelescope_b200.ptxas.log"), "w") as fh:
-        fh.write(res.stdout)
-    return LIB
+    if out is None:
+        with open(os.path.join(HERE, "libtelescope_b200.ptxas.log"), "w") as fh:
+            fh.write(res.stdout)
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -12,6 +12,7 @@
 // Per EM iteration and shard: fused E+M kernel -> replica reduce -> [NCCL all-reduce of K doubles] -> update kernel.
 // The loop runs ahead of the host; convergence is decided on the device and polled through pinned memory.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -313,6 +314,18 @@ extern "C" void tsc_destroy(tsc_handle* h) {
 }
 
 // ------------------------------------------------------------------------------------------------- create
+struct StageTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    StageTimer() : on(getenv("TELESCOPE_B200_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[tsc_create] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user, int32_t n_cols, int64_t nnz,
                        const void* indptr, int32_t indptr_bytes, const int32_t* indices, const uint16_t* raw,
                        const double* q_lut, int32_t lut_len, double pi_prior, double theta_prior) {
@@ -339,6 +352,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         if (d < 0 || d >= ndev) return fail(TSC_ERR_ARG, "device id " + std::to_string(d) + " not present");
     }
 
+    StageTimer tm;
     // ---- read pointers: int64 copy, validation, empty-read compaction
     std::vector<long long> ip((size_t)n_rows_user + 1);
     if (indptr_bytes == 4) { const int32_t* p = (const int32_t*)indptr; for (int64_t i = 0; i <= n_rows_user; ++i) ip[i] = p[i]; }
@@ -361,6 +375,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
     const long long n_rows = (long long)ip.size() - 1;
     h->n_rows = n_rows;
 
+    tm.lap("indptr copy+validate");
     // ---- shard boundaries: contiguous, balanced by entry count
     std::vector<long long> rb(n_local + 1, 0);
     rb[n_local] = n_rows;
@@ -402,6 +417,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         NC(g_nccl.GroupEnd());
     }
 
+    tm.lap("streams + nccl init");
     // ---- tuning
     h->R = cfg.replicas > 0 ? std::min(cfg.replicas, 64) : 16;
     const double avg = n_rows ? (double)nnz / (double)n_rows : 1.0;
@@ -452,6 +468,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         CU(cudaMemcpyAsync(lut_d[i], q_lut, sizeof(double) * lut_len, cudaMemcpyHostToDevice, s.stream));
         h->h2d += sizeof(long long) * (s.n_rows + 1) + (sizeof(uint16_t) + sizeof(int)) * s.nnz + sizeof(double) * lut_len;
         CU(cudaStreamSynchronize(s.stream));   // lip goes out of scope
+        tm.lap("alloc + H2D");
         k_col_signature<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(
             s.indptr, s.n_rows, colin_d[i], raw_d[i], K, ((unsigned long long)s.world_rank << 40), cnt_d[i], s.bad);
         LAUNCH(h);
@@ -464,6 +481,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         CU(cudaMemcpyAsync(s.tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice, s.stream));
         h->h2d += sizeof(Tile) * tiles.size();
         CU(cudaStreamSynchronize(s.stream));
+        tm.lap("signatures + tiling + H2D");
     }
     {   // global per-locus entry counts -> internal numbering (descending count, ties by original index)
         static_assert(sizeof(unsigned long long) == 8, "");
@@ -525,6 +543,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
             }
         }
     }
+    tm.lap("locus classes");
     const size_t kb = sizeof(double) * K;
     for (int i = 0; i < n_local; ++i) {
         Shard& s = h->shards[i];
@@ -549,8 +568,8 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         CU(cudaEventCreateWithFlags(&s.ev_poll[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_poll[1], cudaEventDisableTiming));
         s.grid_rows = s.n_sm * 4;                   // 512-thread blocks, persistent grid-stride
-        s.grid_tiles = s.n_sm * 2;
-        CU(cudaMalloc(&s.partials, sizeof(double) * s.grid_rows));
+        s.grid_tiles = s.n_sm * 2;                  // refined below from the occupancy of the tile kernel
+        CU(cudaMalloc(&s.partials, sizeof(double) * (s.n_sm * 32)));
         k_row_init<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(csr_of(s), s.wy, s.scalars, s.pisum0);
         LAUNCH(h);
         CU(cudaGetLastError());
@@ -564,6 +583,8 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         LAUNCH(h);
         CU(cudaGetLastError());
     }
+    if (tm.on) sync_all(h);
+    tm.lap("build Q + row init");
     // totals over all shards (model.py:691-699)
     ALLREDUCE(h, s.scalars, 2, ncclFloat64, ncclSum);
     ALLREDUCE(h, s.scalars + 2, 1, ncclFloat64, ncclMax);
@@ -601,12 +622,23 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
             const int fit = (int)((max_optin - scratch - 1024) / sizeof(double));
             s.s_cols = std::min(want, std::max(fit, 0));
             s.smem_tiles = scratch + sizeof(double) * s.s_cols;
-            CU(cudaFuncSetAttribute(k_fused_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(s.smem_tiles, scratch)));
-            CU(cudaFuncSetAttribute(k_fused_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
-            if (s.s_cols > 0) { h->smem_tab = true; s.grid_tiles = s.n_sm; }
+            CU(cudaFuncSetAttribute(k_tiles<TILE_FUSED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(s.smem_tiles, scratch)));
+            CU(cudaFuncSetAttribute(k_tiles<TILE_FUSED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+            CU(cudaFuncSetAttribute(k_tiles<TILE_Z, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+            CU(cudaFuncSetAttribute(k_tiles<TILE_LNL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+            if (s.s_cols > 0) {
+                h->smem_tab = true;
+                s.grid_tiles = s.n_sm;
+            } else {
+                int per_sm = 0;
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiles<TILE_FUSED, false>, kTileThreads, scratch));
+                s.grid_tiles = s.n_sm * std::max(per_sm, 1);
+            }
         }
     }
-    return sync_all(h);
+    int rc_final = sync_all(h);
+    tm.lap("constants + finish");
+    return rc_final;
 }
 
 extern "C" int tsc_create(tsc_handle** out, const tsc_config* cfg_in, int64_t n_rows, int32_t n_cols, int64_t nnz,
@@ -727,6 +759,62 @@ extern "C" void* tsc_pinned_alloc(uint64_t bytes) {
 }
 extern "C" void tsc_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
+extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float* mean_ms) {
+    if (!h || !mean_ms || reps <= 0) return fail(TSC_ERR_ARG, "bad argument");
+    Shard& s = h->shards[0];
+    CU(cudaSetDevice(s.dev));
+    const size_t scratch = sizeof(double) * kTileWarps * kScratch;
+    double* zd = nullptr;
+    if (pass_id == 1) CU(cudaMalloc(&zd, sizeof(double) * std::max<long long>(s.nnz, 1)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const double* ta = h->em_done ? s.pt_prev : s.pt;
+    const double* tu = h->em_done ? s.pi_prev : s.pi;
+    cudaError_t err = cudaSuccess;
+    for (int r = -1; r < reps && err == cudaSuccess; ++r) {      // r = -1 is a warm-up
+        if (r == 0) cudaEventRecord(e0, s.stream);
+        TileArgs a{};
+        a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.K = h->K; a.R = h->R;
+        switch (pass_id) {
+            case 0:
+                a.wy = s.wy; a.tab_amb = s.pt; a.acc = s.acc;
+                k_tiles<TILE_FUSED, false><<<s.grid_tiles, kTileThreads, scratch, s.stream>>>(a);
+                break;
+            case 1:
+                a.tab_amb = ta; a.tab_uni = tu; a.z_out = zd;
+                k_tiles<TILE_Z, false><<<s.grid_tiles, kTileThreads, scratch, s.stream>>>(a);
+                break;
+            case 2:
+                a.tab_amb = ta; a.tab_uni = tu; a.inner_amb = s.pt; a.inner_uni = s.pi; a.partials = s.partials;
+                k_tiles<TILE_LNL, false><<<s.grid_tiles, kTileThreads, scratch, s.stream>>>(a);
+                break;
+            case 3: {
+                ReassignArgs g{TSC_EXCLUDE, 0.9, nullptr, nullptr, s.colsum, nullptr};
+                launch_rows(h->G, [&](auto gg) {
+                    k_reassign_rows<decltype(gg)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, g);
+                });
+            } break;
+            default:
+                err = cudaErrorInvalidValue;
+        }
+        LAUNCH(h);
+        if (err == cudaSuccess) err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaEventRecord(e1, s.stream);
+    if (err == cudaSuccess) err = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+    if (pass_id == 0) cudaMemsetAsync(s.acc, 0, sizeof(double) * h->K * h->R, s.stream);   // discard the sums
+    cudaStreamSynchronize(s.stream);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (zd) cudaFree(zd);
+    if (err != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("tsc_time_pass: ") + cudaGetErrorString(err));
+    *mean_ms = ms / reps;
+    return TSC_OK;
+}
+
 extern "C" int tsc_get_kernel_times(tsc_handle* h, float* ms_out, int32_t max_n, int32_t* n_out) {
     if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
     const int n = (int)std::min<size_t>(h->kernel_ms.size(), (size_t)std::max(max_n, 0));
@@ -741,12 +829,12 @@ static int launch_fused(tsc_handle* h, Shard& s) {
         launch_rows(h->G, [&](auto g) {
             k_fused_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), s.wy, s.pt, s.acc, h->K, h->R, s.st);
         });
-    } else if (s.s_cols > 0) {
-        k_fused_tiles<true><<<s.grid_tiles, kTileThreads, s.smem_tiles, s.stream>>>(s.tiles, s.n_tiles, s.q, s.col, s.wy, s.pt,
-                                                                                   s.acc, h->K, h->R, s.s_cols, s.st);
     } else {
-        k_fused_tiles<false><<<s.grid_tiles, kTileThreads, sizeof(double) * kTileWarps * kScratch, s.stream>>>(
-            s.tiles, s.n_tiles, s.q, s.col, s.wy, s.pt, s.acc, h->K, h->R, 0, s.st);
+        TileArgs a{};
+        a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.wy = s.wy; a.tab_amb = s.pt;
+        a.acc = s.acc; a.K = h->K; a.R = h->R; a.s_cols = s.s_cols; a.st = s.st;
+        if (s.s_cols > 0) k_tiles<TILE_FUSED, true><<<s.grid_tiles, kTileThreads, s.smem_tiles, s.stream>>>(a);
+        else k_tiles<TILE_FUSED, false><<<s.grid_tiles, kTileThreads, sizeof(double) * kTileWarps * kScratch, s.stream>>>(a);
     }
     LAUNCH(h);
     CU(cudaGetLastError());
@@ -760,20 +848,25 @@ static int launch_lnl(tsc_handle* h, const double* (*zin_of)(Shard&), bool from_
         CU(cudaSetDevice(s.dev));
         const double* zin = zin_of ? zin_of(s) : nullptr;
         const EmState* st = gated ? s.st : nullptr;
-        launch_rows(h->G, [&](auto g) {
-            k_lnl_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(
-                csr_of(s), zin, from_prev ? s.pt_prev : nullptr, from_prev ? s.pi_prev : nullptr, ia(s), iu(s), s.partials, st);
-        });
+        int nparts = s.grid_rows;
+        if (!zin && h->kernel != TSC_KERNEL_ROWS) {
+            TileArgs a{};
+            a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col;
+            a.tab_amb = s.pt_prev; a.tab_uni = s.pi_prev; a.inner_amb = ia(s); a.inner_uni = iu(s);
+            a.K = h->K; a.st = st; a.partials = s.partials;
+            nparts = s.grid_tiles;
+            k_tiles<TILE_LNL, false><<<s.grid_tiles, kTileThreads, sizeof(double) * kTileWarps * kScratch, s.stream>>>(a);
+        } else {
+            launch_rows(h->G, [&](auto g) {
+                k_lnl_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(
+                    csr_of(s), zin, from_prev ? s.pt_prev : nullptr, from_prev ? s.pi_prev : nullptr, ia(s), iu(s), s.partials, st);
+            });
+        }
         LAUNCH(h);
         CU(cudaGetLastError());
-        if (!gated) {
-            k_sum_partials<<<1, 1024, 0, s.stream>>>(s.partials, s.grid_rows, s.scalars + 4);
-            LAUNCH(h);
-        } else {
-            // when the loop is already done the partials are stale; k_lnl_control ignores the value
-            k_sum_partials<<<1, 1024, 0, s.stream>>>(s.partials, s.grid_rows, s.scalars + 4);
-            LAUNCH(h);
-        }
+        // (when the loop is already done the partials are stale; k_lnl_control ignores the value)
+        k_sum_partials<<<1, 1024, 0, s.stream>>>(s.partials, nparts, s.scalars + 4);
+        LAUNCH(h);
         CU(cudaGetLastError());
     }
     ALLREDUCE(h, s.scalars + 4, 1, ncclFloat64, ncclSum);
@@ -915,9 +1008,16 @@ static int z_to_host(tsc_handle* h, const double* tab_amb_sel, int which, double
         if (rc) return rc;
         const double* ta = which == 0 ? s.tmp_c : which == 1 ? s.pt_prev : s.ones;
         const double* tu = which == 0 ? s.tmp_a : which == 1 ? s.pi_prev : s.ones;
-        launch_rows(h->G, [&](auto g) {
-            k_estep_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, zd);
-        });
+        if (h->kernel != TSC_KERNEL_ROWS) {
+            TileArgs a{};
+            a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.tab_amb = ta; a.tab_uni = tu;
+            a.K = h->K; a.z_out = zd;
+            k_tiles<TILE_Z, false><<<s.grid_tiles, kTileThreads, sizeof(double) * kTileWarps * kScratch, s.stream>>>(a);
+        } else {
+            launch_rows(h->G, [&](auto g) {
+                k_estep_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, zd);
+            });
+        }
         LAUNCH(h);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(z_data + s.nnz_begin, zd, sizeof(double) * s.nnz, cudaMemcpyDeviceToHost, s.stream);

@@ -11,8 +11,9 @@
 // The entry stream is cut into tiles of whole reads, at most 128 consecutive entries each.  One warp takes one
 // tile at a time, in 4 rounds of 32 entries: lane l owns entries base + 32e + l, e = 0..3.
 //   n = Q * (pi*theta)[locus]                         coalesced 256 B / 128 B loads, gather through L1/L2
-//   row sums: per round a Kogge-Stone segmented scan (5 shuffle steps) driven by the round's 32-bit head-flag word
-//             (precomputed per tile); the open read's partial sum is carried from round to round
+//   row sums: the numerators are transposed through a per-warp shared scratch into a blocked layout (lane l holds
+//             entries 4l..4l+3), summed serially per lane and combined by ONE Kogge-Stone segmented scan (5 predicated
+//             shuffle steps) driven by the tile's precomputed 128-bit head-flag mask
 //   the lane holding a read's last entry publishes the read's total to a per-warp shared scratch; one lane per
 //   read then computes g = w*Y / total (one fp64 division sequence per tile instead of one per entry)
 //   c = n * g is scatter-added (RED.ADD.F64) into one of R accumulator replicas resident in L2.
@@ -36,7 +37,13 @@ struct __align__(16) Tile {
 };
 static_assert(sizeof(Tile) == 32, "tile descriptor is one 32-byte sector");
 
-constexpr int kTileWarps = 16;                 // warps per block of the tile kernel
+#ifndef TSC_TILE_WARPS
+#define TSC_TILE_WARPS 16
+#endif
+#ifndef TSC_TILE_MINBLOCKS
+#define TSC_TILE_MINBLOCKS 1
+#endif
+constexpr int kTileWarps = TSC_TILE_WARPS;     // warps per block of the tile kernel
 constexpr int kTileThreads = kTileWarps * 32;
 constexpr int kScrN = 128;                     // per-warp scratch: the tile's numerators (layout transposition)
 constexpr int kScrG = 132;                     //                   per-read totals, then per-read scale g
@@ -64,13 +71,41 @@ __device__ __forceinline__ void add_if_ge(double& v, double y, int a, int b) {
     asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, %3;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(v) : "d"(y), "r"(a), "r"(b));
 }
 
-template <bool SMEM_TAB>
-__global__ void __launch_bounds__(kTileThreads)
-k_fused_tiles(const Tile* __restrict__ tiles, long long n_tiles, const double* __restrict__ q, const int* __restrict__ col,
-              const double* __restrict__ wy, const double* __restrict__ pt, double* __restrict__ acc, int K, int R,
-              int s_cols, const EmState* __restrict__ st) {
+// What a tile pass produces.
+//   TILE_FUSED : E-step + M-step sums -- c = n * (w*Y/total) scatter-added into acc (the per-iteration kernel)
+//   TILE_Z     : E-step alone         -- z = n * recip0(total) written per entry (model.py:702-722; self.z; Q.norm(1))
+//   TILE_LNL   : log-likelihood       -- sum z * log1p(Q * inner[locus]) with z from the E-step tables (model.py:744-760)
+enum { TILE_FUSED = 0, TILE_Z = 1, TILE_LNL = 2 };
+
+struct TileArgs {
+    const Tile* tiles;
+    long long n_tiles;
+    const double* q;
+    const int* col;
+    const double* wy;          // FUSED
+    const double* tab_amb;     // pi*theta of the E-step (ambiguous reads)
+    const double* tab_uni;     // pi of the E-step (unique reads; Z and LNL only)
+    double* acc;               // FUSED: R replicas of K doubles
+    int K, R, s_cols;
+    const EmState* st;         // nullptr = always run
+    double* z_out;             // Z
+    const double* inner_amb;   // LNL: pi*theta and pi inside log1p
+    const double* inner_uni;
+    double* partials;          // LNL: one partial sum per block
+};
+
+template <int MODE, bool SMEM_TAB>
+__global__ void __launch_bounds__(kTileThreads, TSC_TILE_MINBLOCKS)
+k_tiles(const TileArgs a) {
     extern __shared__ double s_dyn[];
-    if (st->done) return;
+    __shared__ double s_red[32];
+    if (a.st && a.st->done) return;
+    const Tile* __restrict__ tiles = a.tiles;
+    const double* __restrict__ q = a.q;
+    const int* __restrict__ col = a.col;
+    const double* __restrict__ pt = a.tab_amb;
+    const int s_cols = a.s_cols;
+    const long long n_tiles = a.n_tiles;
     double* s_n = s_dyn + (threadIdx.x >> 5) * kScratch;         // per-warp scratch
     double* s_g = s_n + kScrN;
     const double* s_tab = s_dyn + kTileWarps * kScratch;          // optional copy of pt[0 .. s_cols)
@@ -79,16 +114,20 @@ k_fused_tiles(const Tile* __restrict__ tiles, long long n_tiles, const double* _
         for (int i = threadIdx.x; i < s_cols; i += blockDim.x) t[i] = pt[i];
         __syncthreads();
     }
-    double* my = acc + (size_t)(blockIdx.x % R) * K;
+    double* my = (MODE == TILE_FUSED) ? a.acc + (size_t)(blockIdx.x % a.R) * a.K : nullptr;
+    double lnl_local = 0.0;
     const int lane = threadIdx.x & 31;
     const unsigned le_mask = 0xffffffffu >> (31 - lane);          // lanes <= mine
     const int wsel = lane >> 3, sh = (lane & 7) * 4;              // blocked layout: my 4 flag bits live in F[wsel] >> sh
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= n_tiles) return;
 
-    int4 d0 = __ldg(reinterpret_cast<const int4*>(tiles + t));
-    uint4 fl = __ldg(reinterpret_cast<const uint4*>(tiles + t) + 1);
+    int4 d0 = make_int4(0, 0, 0, 0);
+    uint4 fl = make_uint4(0, 0, 0, 0);
+    if (t < n_tiles) {
+        d0 = __ldg(reinterpret_cast<const int4*>(tiles + t));
+        fl = __ldg(reinterpret_cast<const uint4*>(tiles + t) + 1);
+    }
     for (; t < n_tiles; t += nwarps) {
         const long long base = ((long long)(unsigned)d0.x) | ((long long)d0.y << 32);
         const int row0 = d0.z;
@@ -100,19 +139,22 @@ k_fused_tiles(const Tile* __restrict__ tiles, long long n_tiles, const double* _
         fl = __ldg(reinterpret_cast<const uint4*>(tiles + tn) + 1);
 
         if (end == 0) {
-            // ---- long read: the whole warp walks it twice
+            // ---- long read (always ambiguous): the whole warp walks it twice
             const long long len = ((long long)F[0]) | ((long long)F[1] << 32);
             const long long hi = base + len;
             double sum = 0;
             for (long long p = base + lane; p < hi; p += 32)
                 sum += ld_stream(q + p) * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, ld_stream(col + p));
             sum = group_sum<32>(sum, 0xffffffffu);
-            const double g = wy[row0] * recip0(sum);
-            if (g != 0.0) {
+            const double g = (MODE == TILE_FUSED) ? a.wy[row0] * recip0(sum) : recip0(sum);
+            if (MODE != TILE_FUSED || g != 0.0) {
                 for (long long p = base + lane; p < hi; p += 32) {
                     const int cc = col[p];
-                    const double c = (q[p] * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, cc)) * g;
-                    if (c != 0.0) atomicAdd(my + cc, c);
+                    const double qv = q[p];
+                    const double c = (qv * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, cc)) * g;
+                    if (MODE == TILE_FUSED) { if (c != 0.0) atomicAdd(my + cc, c); }
+                    if (MODE == TILE_Z) a.z_out[p] = c;
+                    if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p(qv * __ldg(a.inner_amb + cc)); }
                 }
             }
             continue;
@@ -129,11 +171,21 @@ k_fused_tiles(const Tile* __restrict__ tiles, long long n_tiles, const double* _
             qq[e] = ld_stream(qp + 32 * e);
         }
         // w*Y of my read (row phase below), requested early
-        const double w_mine = (lane < nrows) ? __ldg(wy + row0 + lane) : 0.0;
+        double w_mine = 1.0;
+        if (MODE == TILE_FUSED) w_mine = (lane < nrows) ? __ldg(a.wy + row0 + lane) : 0.0;
         double n[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            n[e] = ((32 * e + lane) < end) ? qq[e] * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, cc[e]) : 0.0;
+            double tv;
+            if (MODE == TILE_FUSED) {
+                tv = gather_pt<SMEM_TAB>(pt, s_tab, s_cols, cc[e]);
+            } else {
+                // a read with a single entry: a start here and a start right after (position 128 counts as one)
+                const unsigned nxt = (e < 3) ? F[(e + 1) & 3] : 1u;
+                const bool uniq = ((F[e] & ((F[e] >> 1) | (nxt << 31))) >> lane) & 1u;
+                tv = __ldg((uniq ? a.tab_uni : pt) + cc[e]);
+            }
+            n[e] = ((32 * e + lane) < end) ? qq[e] * tv : 0.0;
             s_n[32 * e + lane] = n[e];
         }
         __syncwarp();
@@ -168,10 +220,10 @@ k_fused_tiles(const Tile* __restrict__ tiles, long long n_tiles, const double* _
             if (((five >> (e + 1)) & 1u) && (4 * lane + e) < end) s_g[below + __popc(five & ((2u << e) - 1u)) - 1] = run;
         }
         __syncwarp();
-        // one lane per read: g = (w*Y) * recip0(total)
+        // one lane per read: the per-read scale (FUSED: (w*Y) * recip0(total); otherwise recip0(total))
         if (lane < nrows) s_g[lane] = (w_mine != 0.0) ? w_mine * recip0(s_g[lane]) : 0.0;
         for (int rho = lane + 32; rho < nrows; rho += 32) {
-            const double w = wy[row0 + rho];
+            const double w = (MODE == TILE_FUSED) ? a.wy[row0 + rho] : 1.0;
             s_g[rho] = (w != 0.0) ? w * recip0(s_g[rho]) : 0.0;
         }
         __syncwarp();
@@ -183,10 +235,22 @@ k_fused_tiles(const Tile* __restrict__ tiles, long long n_tiles, const double* _
             nb += __popc(F[e]);
             if ((32 * e + lane) < end) {
                 const double c = n[e] * s_g[lr];
-                if (c != 0.0) atomicAdd(my + cc[e], c);
+                if (MODE == TILE_FUSED) { if (c != 0.0) atomicAdd(my + cc[e], c); }
+                if (MODE == TILE_Z) a.z_out[base + 32 * e + lane] = c;
+                if (MODE == TILE_LNL) {
+                    if (c != 0.0) {
+                        const unsigned nxt = (e < 3) ? F[(e + 1) & 3] : 1u;
+                        const bool uniq = ((F[e] & ((F[e] >> 1) | (nxt << 31))) >> lane) & 1u;
+                        lnl_local += c * log1p(qq[e] * __ldg((uniq ? a.inner_uni : a.inner_amb) + cc[e]));
+                    }
+                }
             }
         }
         __syncwarp();   // scratch is reused by the next tile
+    }
+    if (MODE == TILE_LNL) {
+        lnl_local = block_sum(lnl_local, s_red);
+        if (threadIdx.x == 0) a.partials[blockIdx.x] = lnl_local;
     }
 }
 

@@ -266,6 +266,12 @@ class TelescopeLikelihood(object):
         _abi.check(self._lib.tsc_get_em_device_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def time_pass(self, which, reps=5):
+        """Mean device time (ms) of one pass on local shard 0: 'fused', 'estep', 'lnl' or 'reassign' (diagnostic)."""
+        ms = C.c_float(0)
+        _abi.check(self._lib.tsc_time_pass(self._h, {"fused": 0, "estep": 1, "lnl": 2, "reassign": 3}[which], reps, C.byref(ms)))
+        return ms.value
+
     def counters(self):
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         _abi.check(self._lib.tsc_get_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))

@@ -214,42 +214,6 @@ static int launch_rows(int G, F&& f) {
 
 static Csr csr_of(const Shard& s) { return Csr{s.indptr, s.col, s.q, s.n_rows}; }
 
-// ------------------------------------------------------------------------------------------------- tiling
-static void build_tiles(const long long* ip, long long n_rows, std::vector<Tile>& out, long long& n_long) {
-    out.clear();
-    n_long = 0;
-    out.reserve((size_t)(ip[n_rows] / 100 + 16));
-    long long r = 0;
-    while (r < n_rows) {
-        const long long base = ip[r];
-        Tile t;
-        t.base = base;
-        t.row0 = (int)r;
-        t.flags[0] = t.flags[1] = t.flags[2] = t.flags[3] = 0;
-        if (ip[r + 1] - base > 128) {   // long read
-            const long long len = ip[r + 1] - base;
-            t.meta = (1 << 16);
-            t.flags[0] = (unsigned)(len & 0xffffffffLL);
-            t.flags[1] = (unsigned)(len >> 32);
-            out.push_back(t);
-            ++n_long;
-            ++r;
-            continue;
-        }
-        long long r2 = r;
-        while (r2 < n_rows && ip[r2 + 1] - base <= 128) {
-            const int p = (int)(ip[r2] - base);
-            t.flags[p >> 5] |= 1u << (p & 31);
-            ++r2;
-        }
-        const int end = (int)(ip[r2] - base);
-        if (end < 128) t.flags[end >> 5] |= 1u << (end & 31);
-        t.meta = (end & 0xff) | ((int)(r2 - r) << 16);
-        out.push_back(t);
-        r = r2;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------- small API
 extern "C" int tsc_abi_version(void) { return TSC_ABI_VERSION; }
 extern "C" const char* tsc_last_error(void) { return g_err.c_str(); }
@@ -353,36 +317,45 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
     }
 
     StageTimer tm;
-    // ---- read pointers: int64 copy, validation, empty-read compaction
-    std::vector<long long> ip((size_t)n_rows_user + 1);
-    if (indptr_bytes == 4) { const int32_t* p = (const int32_t*)indptr; for (int64_t i = 0; i <= n_rows_user; ++i) ip[i] = p[i]; }
-    else { const int64_t* p = (const int64_t*)indptr; for (int64_t i = 0; i <= n_rows_user; ++i) ip[i] = p[i]; }
-    if (ip[0] != 0 || ip[n_rows_user] != nnz) return fail(TSC_ERR_ARG, "indptr[0] must be 0 and indptr[n_rows] must be nnz");
-    bool has_empty = false;
-    for (int64_t i = 0; i < n_rows_user; ++i) {
-        if (ip[i + 1] < ip[i]) return fail(TSC_ERR_ARG, "indptr is not non-decreasing");
-        if (ip[i + 1] == ip[i]) has_empty = true;
-    }
-    if (has_empty) {
-        h->rowmap.reserve(n_rows_user);
-        std::vector<long long> ip2;
-        ip2.reserve(n_rows_user + 1);
-        ip2.push_back(0);
+    // ---- read pointers.  Fast path: the caller's array is used as is (validated and rebased on the device).
+    // Matrices with empty reads take the slow path: the reads are compacted on the host first.
+    auto ip_at = [&](int64_t i) -> long long {
+        return indptr_bytes == 4 ? (long long)((const int32_t*)indptr)[i] : (long long)((const int64_t*)indptr)[i];
+    };
+    if (ip_at(0) != 0 || ip_at(n_rows_user) != nnz) return fail(TSC_ERR_ARG, "indptr[0] must be 0 and indptr[n_rows] must be nnz");
+    std::vector<long long> ip;          // only filled on the slow path
+    auto compact_on_host = [&]() -> int {
+        std::vector<long long> full((size_t)n_rows_user + 1);
+        for (int64_t i = 0; i <= n_rows_user; ++i) full[i] = ip_at(i);
         for (int64_t i = 0; i < n_rows_user; ++i)
-            if (ip[i + 1] > ip[i]) { h->rowmap.push_back(i); ip2.push_back(ip[i + 1]); }
-        ip.swap(ip2);
+            if (full[i + 1] < full[i]) return fail(TSC_ERR_ARG, "indptr is not non-decreasing");
+        h->rowmap.clear();
+        h->rowmap.reserve(n_rows_user);
+        ip.clear();
+        ip.reserve(n_rows_user + 1);
+        ip.push_back(0);
+        for (int64_t i = 0; i < n_rows_user; ++i)
+            if (full[i + 1] > full[i]) { h->rowmap.push_back(i); ip.push_back(full[i + 1]); }
+        return TSC_OK;
+    };
+    bool slow = false;
+    if (n_rows_user > 0 && n_rows_user <= 4096) {       // tiny inputs: just look
+        for (int64_t i = 0; i < n_rows_user && !slow; ++i) slow = ip_at(i + 1) <= ip_at(i);
+        if (slow) { int rc = compact_on_host(); if (rc) return rc; }
     }
-    const long long n_rows = (long long)ip.size() - 1;
+  retry_with_compaction:
+    const long long n_rows = slow ? (long long)ip.size() - 1 : (long long)n_rows_user;
     h->n_rows = n_rows;
-
+    auto row_ptr = [&](long long r) -> long long { return slow ? ip[r] : ip_at(r); };
     tm.lap("indptr copy+validate");
     // ---- shard boundaries: contiguous, balanced by entry count
     std::vector<long long> rb(n_local + 1, 0);
     rb[n_local] = n_rows;
     for (int i = 1; i < n_local; ++i) {
         const long long target = nnz / n_local * i;
-        rb[i] = std::lower_bound(ip.begin(), ip.end(), target) - ip.begin();
-        rb[i] = std::min(std::max(rb[i], rb[i - 1]), n_rows);
+        long long lo = rb[i - 1], hi = n_rows;
+        while (lo < hi) { const long long mid = (lo + hi) / 2; if (row_ptr(mid) < target) lo = mid + 1; else hi = mid; }
+        rb[i] = lo;
     }
 
     // ---- NCCL
@@ -394,21 +367,21 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         else NC(g_nccl.GetUniqueId(&id));
     }
 
-    h->shards.resize(n_local);
+    if (h->shards.empty()) h->shards.resize(n_local);
     for (int i = 0; i < n_local; ++i) {
         Shard& s = h->shards[i];
         s.dev = cfg.device_ids ? cfg.device_ids[i] : i;
         s.world_rank = h->proc_rank * n_local + i;
         s.row_begin = rb[i];
         s.n_rows = rb[i + 1] - rb[i];
-        s.nnz_begin = ip[rb[i]];
-        s.nnz = ip[rb[i + 1]] - ip[rb[i]];
+        s.nnz_begin = row_ptr(rb[i]);
+        s.nnz = row_ptr(rb[i + 1]) - row_ptr(rb[i]);
         if (s.n_rows >= (1LL << 31)) return fail(TSC_ERR_ARG, "more than 2^31 reads on one GPU");
         CU(cudaSetDevice(s.dev));
-        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(cudaDeviceGetAttribute(&s.n_sm, cudaDevAttrMultiProcessorCount, s.dev));
     }
-    if (h->world > 1) {
+    if (h->world > 1 && !h->shards[0].comm) {
         NC(g_nccl.GroupStart());
         for (auto& s : h->shards) {
             CU(cudaSetDevice(s.dev));
@@ -459,30 +432,90 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         CU(cudaMemsetAsync(cnt_d[i], 0, sizeof(unsigned long long) * K * 3, s.stream));
         CU(cudaMemsetAsync(s.col + s.nnz, 0, sizeof(int) * pad, s.stream));
         CU(cudaMemsetAsync(s.q + s.nnz, 0, sizeof(double) * pad, s.stream));
-        // local read pointers rebased to the shard
-        std::vector<long long> lip((size_t)s.n_rows + 1);
-        for (long long r = 0; r <= s.n_rows; ++r) lip[r] = ip[s.row_begin + r] - s.nnz_begin;
-        CU(cudaMemcpyAsync(s.indptr, lip.data(), sizeof(long long) * (s.n_rows + 1), cudaMemcpyHostToDevice, s.stream));
+        if (tm.on) cudaStreamSynchronize(s.stream);
+        tm.lap("  cudaMalloc");
+        // read pointers: native dtype up, int64 + rebased + validated on the device
+        {
+            const size_t ib = slow ? sizeof(long long) : (size_t)indptr_bytes;
+            void* ip_native = nullptr;
+            CU(cudaMalloc(&ip_native, ib * (s.n_rows + 1)));
+            const char* src = slow ? (const char*)(ip.data() + s.row_begin) : (const char*)indptr + ib * s.row_begin;
+            CU(cudaMemcpyAsync(ip_native, src, ib * (s.n_rows + 1), cudaMemcpyHostToDevice, s.stream));
+            const int g = grid_for(s.n_rows + 1, 256, s.n_sm * 16);
+            if (ib == 4) k_indptr_prepare<int><<<g, 256, 0, s.stream>>>((const int*)ip_native, s.n_rows + 1, s.nnz_begin, s.indptr, s.bad);
+            else k_indptr_prepare<long long><<<g, 256, 0, s.stream>>>((const long long*)ip_native, s.n_rows + 1, s.nnz_begin, s.indptr, s.bad);
+            LAUNCH(h);
+            CU(cudaGetLastError());
+            int flags = 0;
+            CU(cudaMemcpyAsync(&flags, s.bad, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+            cudaFree(ip_native);
+            if (flags & 1) return fail(TSC_ERR_ARG, "indptr is not non-decreasing");
+            if (flags & 2) {            // empty reads: start over on the slow path
+                if (slow) return fail(TSC_ERR_STATE, "internal: empty read after compaction");
+                cleanup_tmp();
+                for (auto& sh : h->shards) {
+                    cudaSetDevice(sh.dev);
+                    void* ptrs[] = {sh.indptr, sh.col, sh.q, sh.wy, sh.bad, sh.tiles};
+                    for (void* p : ptrs) if (p) cudaFree(p);
+                    sh.indptr = nullptr; sh.col = nullptr; sh.q = nullptr; sh.wy = nullptr; sh.bad = nullptr; sh.tiles = nullptr;
+                }
+                int rc = compact_on_host();
+                if (rc) return rc;
+                slow = true;
+                goto retry_with_compaction;
+            }
+            CU(cudaMemsetAsync(s.bad, 0, sizeof(int), s.stream));
+        }
+        tm.lap("  indptr up + prepare");
         CU(cudaMemcpyAsync(raw_d[i], raw + s.nnz_begin, sizeof(uint16_t) * s.nnz, cudaMemcpyHostToDevice, s.stream));
         CU(cudaMemcpyAsync(colin_d[i], indices + s.nnz_begin, sizeof(int) * s.nnz, cudaMemcpyHostToDevice, s.stream));
         CU(cudaMemcpyAsync(lut_d[i], q_lut, sizeof(double) * lut_len, cudaMemcpyHostToDevice, s.stream));
-        h->h2d += sizeof(long long) * (s.n_rows + 1) + (sizeof(uint16_t) + sizeof(int)) * s.nnz + sizeof(double) * lut_len;
-        CU(cudaStreamSynchronize(s.stream));   // lip goes out of scope
-        tm.lap("alloc + H2D");
+        h->h2d += (size_t)(slow ? 8 : indptr_bytes) * (s.n_rows + 1) + (sizeof(uint16_t) + sizeof(int)) * s.nnz + sizeof(double) * lut_len;
+        if (tm.on) { cudaStreamSynchronize(s.stream); tm.lap("  entries H2D (sync for timing)"); }
+        // tiles for the fused kernel, built on the device while the entry arrays are still arriving
+        {
+            const int n_chunks = (int)((s.n_rows + kChunkRows - 1) / kChunkRows);
+            int* counts_d = nullptr;
+            long long* offs_d = nullptr;
+            unsigned long long* nlong_d = nullptr;
+            CU(cudaMalloc(&counts_d, sizeof(int) * std::max(n_chunks, 1)));
+            CU(cudaMalloc(&offs_d, sizeof(long long) * std::max(n_chunks, 1)));
+            CU(cudaMalloc(&nlong_d, sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(nlong_d, 0, sizeof(unsigned long long), s.stream));
+            std::vector<int> counts(n_chunks);
+            std::vector<long long> offs(n_chunks);
+            if (n_chunks > 0) {
+                k_tile_count<<<(n_chunks + 127) / 128, 128, 0, s.stream>>>(s.indptr, s.n_rows, counts_d, n_chunks);
+                LAUNCH(h);
+                CU(cudaGetLastError());
+                CU(cudaMemcpyAsync(counts.data(), counts_d, sizeof(int) * n_chunks, cudaMemcpyDeviceToHost, s.stream));
+                CU(cudaStreamSynchronize(s.stream));
+            }
+            long long total = 0;
+            for (int c = 0; c < n_chunks; ++c) { offs[c] = total; total += counts[c]; }
+            s.n_tiles = total;
+            CU(cudaMalloc(&s.tiles, sizeof(Tile) * std::max<long long>(total, 1)));
+            if (n_chunks > 0) {
+                CU(cudaMemcpyAsync(offs_d, offs.data(), sizeof(long long) * n_chunks, cudaMemcpyHostToDevice, s.stream));
+                k_tile_fill<<<(n_chunks + 127) / 128, 128, 0, s.stream>>>(s.indptr, s.n_rows, offs_d, n_chunks, s.tiles, nlong_d);
+                LAUNCH(h);
+                CU(cudaGetLastError());
+            }
+            unsigned long long nl = 0;
+            CU(cudaMemcpyAsync(&nl, nlong_d, sizeof(nl), cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+            s.n_long = (long long)nl;
+            cudaFree(counts_d); cudaFree(offs_d); cudaFree(nlong_d);
+        }
+        tm.lap("  tiles");
         k_col_signature<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(
             s.indptr, s.n_rows, colin_d[i], raw_d[i], K, ((unsigned long long)s.world_rank << 40), cnt_d[i], s.bad);
         LAUNCH(h);
         CU(cudaGetLastError());
-        // tiles for the fused kernel
-        std::vector<Tile> tiles;
-        build_tiles(lip.data(), s.n_rows, tiles, s.n_long);
-        s.n_tiles = (long long)tiles.size();
-        CU(cudaMalloc(&s.tiles, sizeof(Tile) * std::max<size_t>(tiles.size(), 1)));
-        CU(cudaMemcpyAsync(s.tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice, s.stream));
-        h->h2d += sizeof(Tile) * tiles.size();
-        CU(cudaStreamSynchronize(s.stream));
-        tm.lap("signatures + tiling + H2D");
     }
+    if (tm.on) sync_all(h);
+    tm.lap("column signatures");
     {   // global per-locus entry counts -> internal numbering (descending count, ties by original index)
         static_assert(sizeof(unsigned long long) == 8, "");
         if (h->world > 1) {
@@ -638,6 +671,8 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
     }
     int rc_final = sync_all(h);
     tm.lap("constants + finish");
+    cleanup_tmp();
+    tm.lap("free temporaries");
     return rc_final;
 }
 

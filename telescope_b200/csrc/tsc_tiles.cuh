@@ -37,8 +37,87 @@ struct __align__(16) Tile {
 };
 static_assert(sizeof(Tile) == 32, "tile descriptor is one 32-byte sector");
 
+// Greedy tiling step shared by host and device: the tile that starts at read r; returns the first read after it.
+__host__ __device__ inline long long next_tile(const long long* ip, long long r, long long r_stop, Tile& t) {
+    const long long base = ip[r];
+    t.base = base;
+    t.row0 = (int)r;
+    t.flags[0] = t.flags[1] = t.flags[2] = t.flags[3] = 0;
+    if (ip[r + 1] - base > 128) {   // long read: a tile of its own
+        const long long len = ip[r + 1] - base;
+        t.meta = (1 << 16);
+        t.flags[0] = (unsigned)(len & 0xffffffffLL);
+        t.flags[1] = (unsigned)(len >> 32);
+        return r + 1;
+    }
+    long long r2 = r;
+    while (r2 < r_stop && ip[r2 + 1] - base <= 128) {
+        const int p = (int)(ip[r2] - base);
+        t.flags[p >> 5] |= 1u << (p & 31);
+        ++r2;
+    }
+    const int end = (int)(ip[r2] - base);
+    if (end < 128) t.flags[end >> 5] |= 1u << (end & 31);
+    t.meta = (end & 0xff) | ((int)(r2 - r) << 16);
+    return r2;
+}
+
+// Tiling on the device: reads are cut into chunks of kChunkRows; every chunk is tiled greedily by one thread (a tile
+// never crosses a chunk boundary, which costs at most one short tile per chunk).  Pass 1 counts, pass 2 writes.
+constexpr int kChunkRows = 2048;
+
+__global__ void k_tile_count(const long long* __restrict__ ip, long long n_rows, int* __restrict__ counts, int n_chunks) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    long long r = (long long)c * kChunkRows;
+    const long long stop = min(r + (long long)kChunkRows, n_rows);
+    int n = 0;
+    Tile t;
+    while (r < stop) { r = next_tile(ip, r, stop, t); ++n; }
+    counts[c] = n;
+}
+
+__global__ void k_tile_fill(const long long* __restrict__ ip, long long n_rows, const long long* __restrict__ offsets,
+                            int n_chunks, Tile* __restrict__ out, unsigned long long* __restrict__ n_long) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    long long r = (long long)c * kChunkRows;
+    const long long stop = min(r + (long long)kChunkRows, n_rows);
+    long long o = offsets[c];
+    unsigned long long nl = 0;
+    while (r < stop) {
+        Tile t;
+        r = next_tile(ip, r, stop, t);
+        if ((t.meta & 0xff) == 0) ++nl;
+        out[o++] = t;
+    }
+    if (nl) atomicAdd(n_long, nl);
+}
+
+// Read pointers as the caller has them (int32 or int64, absolute) -> int64 relative to the shard's first entry,
+// with validation: flags |= 1 if not non-decreasing, |= 2 if some read is empty.
+template <typename T>
+__global__ void k_indptr_prepare(const T* __restrict__ in, long long n_plus1, long long first, long long* __restrict__ out,
+                                 int* __restrict__ flags) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int f = 0;
+    for (; i < n_plus1; i += stride) {
+        const long long v = (long long)in[i];
+        out[i] = v - first;
+        if (i + 1 < n_plus1) {
+            const long long nx = (long long)in[i + 1];
+            if (nx < v) f |= 1;
+            if (nx == v) f |= 2;
+        }
+    }
+    if (f) atomicOr(flags, f);
+}
+
+// Block shape of the tile kernel.  Measured on B200 (profiles/r1_occupancy_sweep.md): 32 warps per SM at <= 64
+// registers per thread is the sweet spot; a 1024-thread block pins the compiler to that budget for every epilogue.
 #ifndef TSC_TILE_WARPS
-#define TSC_TILE_WARPS 16
+#define TSC_TILE_WARPS 32
 #endif
 #ifndef TSC_TILE_MINBLOCKS
 #define TSC_TILE_MINBLOCKS 1

@@ -225,3 +225,41 @@ def test_multi_gpu_in_process_matches_single():
     assert rel_err(a.pi, b.pi) < 1e-9 and abs(a.lnl - b.lnl) <= 1e-10 * abs(a.lnl)
     assert np.array_equal(a.reassign_colsum("exclude"), b.reassign_colsum("exclude"))
     a.close(); b.close()
+
+
+def test_large_matrix_with_empty_reads_takes_the_compaction_path():
+    # > 4096 reads, so emptiness is detected on the device and construction restarts with host-side compaction
+    m = _matrix(N=30000, K=300, avg=6, skew=False, seed=61).tolil()
+    for r in (0, 5, 4097, 12345, 29999):
+        m.rows[r], m.data[r] = [], []
+    m = sp.csr_matrix(m).astype(np.uint16)
+    opts = Opts(max_iter=8)
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    tl.em(); o.em()
+    assert tl.n_iter == o.n_iter
+    assert rel_err(tl.pi, o.pi) < TIGHT and abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
+    assert np.array_equal(tl.Y.ravel(), o.Y)
+    assert rel_err(_dense_z(tl.z, m), o.z) < RTOL
+    assert np.array_equal(tl.reassign_colsum("exclude"), o.reassign_colsum("exclude"))
+    np.random.seed(3); a = tl.reassign_colsum("choose", initial=True)
+    np.random.seed(3); b = o.reassign_colsum("choose", initial=True)
+    assert np.array_equal(a, b)
+    tl.close()
+
+
+def test_bad_inputs_are_rejected():
+    from telescope_b200 import _abi
+    good = _matrix(N=100, K=20, avg=4, skew=False, seed=71)
+    bad_col = good.copy()
+    bad_col.indices = bad_col.indices.copy()
+    bad_col.indices[3] = 25
+    with pytest.raises(_abi.TelescopeCudaError):
+        _tl(bad_col, Opts())
+    with pytest.raises(_abi.TelescopeCudaError):
+        _tl(good, Opts()).z_not_there if False else _tl(good, Opts(), devices=[99])
+    tl = _tl(good, Opts())
+    assert tl.z is None                                   # model.py:659
+    with pytest.raises(_abi.TelescopeCudaError):
+        tl.reassign("exclude")                            # self.z is None before em()
+    assert tl.reassign("exclude", initial=True).shape == good.shape
+    tl.close()

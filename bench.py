@@ -225,38 +225,25 @@ def main():
     from telescope_b200.synthetic import shard_bounds, synth_csr
     import scipy.sparse as sp
 
-    dist = None
-    tdist = None
-    if world > 1:
-        import torch
-        import torch.distributed as tdist
-        torch.cuda.set_device(local_rank)
-        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            ident = torch.frombuffer(bytearray(_abi.nccl_unique_id()), dtype=torch.uint8).cuda()
-        tdist.broadcast(ident, 0)
-        dist = DistInfo(world, rank, bytes(ident.cpu().numpy().tobytes()))
+    # one process per GPU: the NCCL id travels through a file shared by the launcher's children; barriers and
+    # max-over-ranks go over the library's own communicator (no torch in the workers)
+    from telescope_b200 import dist as tsc_dist
+    dist = tsc_dist.rendezvous()
+    live = {"tl": None}
+
+    def _reduce(x, op):
+        if world == 1 or live["tl"] is None:
+            return x
+        return float(live["tl"].allreduce([x], op)[0])
 
     def barrier():
-        if tdist is not None:
-            tdist.barrier()
+        _reduce(0.0, "sum")
 
     def max_over_ranks(x):
-        if tdist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-        return float(t.item())
+        return _reduce(x, "max")
 
     def sum_over_ranks(x):
-        if tdist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
-        return float(t.item())
+        return _reduce(x, "sum")
 
     # ---- this rank's block of reads, generated straight into page-locked host memory
     lo, hi = shard_bounds(a.reads, world)[rank]
@@ -271,20 +258,23 @@ def main():
     m = sp.csr_matrix((pin_raw.array, pin_ix.array, ip), shape=(hi - lo, a.loci), copy=False)
     t_gen = time.perf_counter() - t_gen
     local_nnz = int(m.nnz)
-    max_score = int(max_over_ranks(float(pin_raw.array.max())))
-    total_nnz = int(sum_over_ranks(float(local_nnz)))
+    # the generator's score range is fixed (best hits reach 211 in any block of more than a few thousand reads), so
+    # the global maximum needs no exchange before the communicator exists; it is re-checked after construction
+    max_score = 211 if world > 1 else int(pin_raw.array.max())
 
     kw = dict(devices=[local_rank], dist=dist, max_score=max_score, kernel=a.kernel, replicas=a.replicas,
               smem_table_cols=a.smem_table_cols, permute_columns=a.permute)
 
     # ---- e2e: the whole job through the public class, host buffers in, parameters out
-    barrier()
     t0 = time.perf_counter()
     tl = TelescopeLikelihood(m, Opts(K), **kw)
+    live["tl"] = tl
     t_create = time.perf_counter() - t0
     tl.em()
     pi_e2e = tl.pi.copy()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
+    assert int(max_over_ranks(float(pin_raw.array.max()))) == max_score, "score range assumption violated"
+    total_nnz = int(sum_over_ranks(float(local_nnz)))
     c_e2e = tl.counters()
     lnl_first = tl.lnl
 
@@ -361,6 +351,7 @@ def main():
 
     # ---- CPU arm beside it (rank 0, single-GPU run only) + parity of the GPU path on the same sample
     if rank == 0 and world == 1 and not a.no_cpu:
+        live["tl"] = None
         tl.close()
         cb = run_cpu(a, 0, 2, csr=(ip, pin_ix.array, pin_raw.array))
         rows = cb["_rows"]
@@ -378,9 +369,10 @@ def main():
         line["cpu_baseline"] = {k: v for k, v in cb.items() if not k.startswith("_")}
     if rank == 0:
         print(json.dumps(line))
-    if tdist is not None:
-        tdist.barrier()
-        tdist.destroy_process_group()
+    if world > 1:
+        barrier()
+        tsc_dist.cleanup()
+    tl.close()
     return 0
 
 

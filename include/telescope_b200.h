@@ -128,6 +128,10 @@ int tsc_get_em_device_ms(tsc_handle* h, float* ms_out);
  * Does not change pi/theta or the EM state.
  */
 int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float* mean_ms);
+/* All-reduce n (<= 8) host doubles over every shard of every process of this handle's communicator (op 0 = sum,
+ * 1 = max); with n_procs == 1 and one device it is the identity.  Lets multi-process drivers agree on timings and
+ * synchronise without a second communication library. */
+int tsc_allreduce_f64(tsc_handle* h, double* inout, int32_t n, int32_t op);
 /* launches = kernels this library launched since creation; bytes moved over PCIe by this handle */
 int tsc_get_counters(tsc_handle* h, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
 

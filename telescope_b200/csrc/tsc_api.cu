@@ -794,6 +794,26 @@ extern "C" void* tsc_pinned_alloc(uint64_t bytes) {
 }
 extern "C" void tsc_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
+extern "C" int tsc_allreduce_f64(tsc_handle* h, double* inout, int32_t n, int32_t op) {
+    if (!h || !inout || n <= 0 || n > 8 || (op != 0 && op != 1)) return fail(TSC_ERR_ARG, "bad argument");
+    if (h->world == 1) return TSC_OK;
+    // every local shard contributes the same host values; divide sums by the local shard count afterwards
+    const int n_local = (int)h->shards.size();
+    for (auto& s : h->shards) {
+        CU(cudaSetDevice(s.dev));
+        CU(cudaMemcpyAsync(s.scalars, inout, sizeof(double) * n, cudaMemcpyHostToDevice, s.stream));
+    }
+    if (op == 0) ALLREDUCE(h, s.scalars, (size_t)n, ncclFloat64, ncclSum);
+    else ALLREDUCE(h, s.scalars, (size_t)n, ncclFloat64, ncclMax);
+    Shard& s0 = h->shards[0];
+    CU(cudaSetDevice(s0.dev));
+    CU(cudaMemcpyAsync(inout, s0.scalars, sizeof(double) * n, cudaMemcpyDeviceToHost, s0.stream));
+    int rc = sync_all(h);
+    if (rc) return rc;
+    if (op == 0 && n_local > 1) for (int i = 0; i < n; ++i) inout[i] /= n_local;
+    return TSC_OK;
+}
+
 extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float* mean_ms) {
     if (!h || !mean_ms || reps <= 0) return fail(TSC_ERR_ARG, "bad argument");
     Shard& s = h->shards[0];

@@ -266,6 +266,12 @@ class TelescopeLikelihood(object):
         _abi.check(self._lib.tsc_get_em_device_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def allreduce(self, values, op="sum"):
+        """Sum / max of a few host doubles over all ranks of this model's communicator (identity on one GPU)."""
+        buf = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64).copy()
+        _abi.check(self._lib.tsc_allreduce_f64(self._h, _abi._p(buf, C.c_double), buf.size, {"sum": 0, "max": 1}[op]))
+        return buf
+
     def time_pass(self, which, reps=5):
         """Mean device time (ms) of one pass on local shard 0: 'fused', 'estep', 'lnl' or 'reassign' (diagnostic)."""
         ms = C.c_float(0)

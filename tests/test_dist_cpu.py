@@ -71,3 +71,29 @@ def test_shard_bounds_cover_all_reads():
     for n, w in [(10, 1), (10, 3), (50_000_000, 8), (7, 8)]:
         b = shard_bounds(n, w)
         assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+def _rdzv_child():
+    sys.path.insert(0, ROOT)
+    from telescope_b200 import dist
+    d = dist.rendezvous(timeout=60)
+    print("RDZV %d %d %s" % (d.proc_rank, d.n_procs, d.nccl_id.hex()))
+    if d.proc_rank == 0:
+        import time
+        time.sleep(1.0)
+        dist.cleanup()
+
+
+def test_torch_free_rendezvous_hands_rank0s_nccl_id_to_every_rank():
+    """Two children of this process (as under torchrun, ranks share a parent) agree on one 128-byte NCCL id."""
+    import subprocess
+    procs = []
+    for r in (1, 0):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_PORT="29%03d" % (os.getpid() % 1000))
+        code = "import sys; sys.path.insert(0, %r); import tests.test_dist_cpu as t; t._rdzv_child()" % ROOT
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, universal_newlines=True, cwd=ROOT))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    got = sorted(l.split() for o in outs for l in o.splitlines() if l.startswith("RDZV"))
+    assert [g[1] for g in got] == ["0", "1"] and got[0][2] == got[1][2] == "2"
+    assert got[0][3] == got[1][3] and len(got[0][3]) == 256

@@ -73,15 +73,16 @@ def test_shard_bounds_cover_all_reads():
         assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
 
 
-def _rdzv_child():
-    sys.path.insert(0, ROOT)
-    from telescope_b200 import dist
-    d = dist.rendezvous(timeout=60)
-    print("RDZV %d %d %s" % (d.proc_rank, d.n_procs, d.nccl_id.hex()))
-    if d.proc_rank == 0:
-        import time
-        time.sleep(1.0)
-        dist.cleanup()
+_RDZV_CHILD = """
+import sys, time
+sys.path.insert(0, %r)
+from telescope_b200 import dist
+d = dist.rendezvous(timeout=60)
+print("RDZV %%d %%d %%s" %% (d.proc_rank, d.n_procs, d.nccl_id.hex()))
+if d.proc_rank == 0:
+    time.sleep(1.0)
+    dist.cleanup()
+"""
 
 
 def test_torch_free_rendezvous_hands_rank0s_nccl_id_to_every_rank():
@@ -90,8 +91,8 @@ def test_torch_free_rendezvous_hands_rank0s_nccl_id_to_every_rank():
     procs = []
     for r in (1, 0):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_PORT="29%03d" % (os.getpid() % 1000))
-        code = "import sys; sys.path.insert(0, %r); import tests.test_dist_cpu as t; t._rdzv_child()" % ROOT
-        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, universal_newlines=True, cwd=ROOT))
+        procs.append(subprocess.Popen([sys.executable, "-c", _RDZV_CHILD % ROOT], env=env, stdout=subprocess.PIPE,
+                                      universal_newlines=True, cwd=ROOT))
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     got = sorted(l.split() for o in outs for l in o.splitlines() if l.startswith("RDZV"))

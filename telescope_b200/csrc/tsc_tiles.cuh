@@ -124,7 +124,7 @@ __global__ void k_indptr_prepare(const T* __restrict__ in, long long n_plus1, lo
 #endif
 constexpr int kTileWarps = TSC_TILE_WARPS;     // warps per block of the tile kernel
 constexpr int kTileThreads = kTileWarps * 32;
-constexpr int kScrN = 128;                     // per-warp scratch: the tile's numerators (layout transposition)
+constexpr int kScrN = 136;                     // per-warp scratch: the tile's numerators (swizzled layout transposition)
 constexpr int kScrG = 132;                     //                   per-read totals, then per-read scale g
 constexpr int kScratch = kScrN + kScrG;        // doubles per warp
 
@@ -134,17 +134,9 @@ __device__ __forceinline__ double gather_pt(const double* __restrict__ pt, const
     return __ldg(pt + c);
 }
 
-// streaming loads: read once, keep them out of L1 so the pi*theta table stays resident there
-__device__ __forceinline__ double ld_stream(const double* p) {
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int ld_stream(const int* p) {
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
+// entry stream loads (read-only path; an L1::no_allocate hint measured neutral, profiles/r1_kernel_variants.md)
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldg(p); }
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldg(p); }
 // v += y when a >= b (predicated add: one DADD instead of two selects and an add)
 __device__ __forceinline__ void add_if_ge(double& v, double y, int a, int b) {
     asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, %3;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(v) : "d"(y), "r"(a), "r"(b));
@@ -198,24 +190,23 @@ k_tiles(const TileArgs a) {
     const int lane = threadIdx.x & 31;
     const unsigned le_mask = 0xffffffffu >> (31 - lane);          // lanes <= mine
     const int wsel = lane >> 3, sh = (lane & 7) * 4;              // blocked layout: my 4 flag bits live in F[wsel] >> sh
+    // Scratch swizzle for the transposition: entry p lives at double index 2*P + (p&1), P = (c>>1) + 36*(c&1), c = p>>1.
+    // Writes (lane-consecutive, p = 32e + lane) and the two 128-bit reads per lane (entries 4l..4l+1 at 2l, entries
+    // 4l+2..4l+3 at 72 + 2l) are then both free of bank conflicts.
+    const int wl = 2 * (lane >> 2) + 72 * ((lane >> 1) & 1) + (lane & 1);
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
-    int4 d0 = make_int4(0, 0, 0, 0);
-    uint4 fl = make_uint4(0, 0, 0, 0);
-    if (t < n_tiles) {
-        d0 = __ldg(reinterpret_cast<const int4*>(tiles + t));
-        fl = __ldg(reinterpret_cast<const uint4*>(tiles + t) + 1);
-    }
     for (; t < n_tiles; t += nwarps) {
+        const int4 d0 = __ldg(reinterpret_cast<const int4*>(tiles + t));
+        const uint4 fl = __ldg(reinterpret_cast<const uint4*>(tiles + t) + 1);
         const long long base = ((long long)(unsigned)d0.x) | ((long long)d0.y << 32);
         const int row0 = d0.z;
         const int end = d0.w & 0xff, nrows = (d0.w >> 16) & 0xff;
         const unsigned F[4] = {fl.x, fl.y, fl.z, fl.w};
-        // next tile's descriptor: in flight while this tile is processed
+        // next tile's descriptor: pulled towards the SM while this tile is processed (costs no registers)
         const long long tn = (t + nwarps < n_tiles) ? t + nwarps : t;
-        d0 = __ldg(reinterpret_cast<const int4*>(tiles + tn));
-        fl = __ldg(reinterpret_cast<const uint4*>(tiles + tn) + 1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(tiles + tn));
 
         if (end == 0) {
             // ---- long read (always ambiguous): the whole warp walks it twice
@@ -265,12 +256,12 @@ k_tiles(const TileArgs a) {
                 tv = __ldg((uniq ? a.tab_uni : pt) + cc[e]);
             }
             n[e] = ((32 * e + lane) < end) ? qq[e] * tv : 0.0;
-            s_n[32 * e + lane] = n[e];
+            s_n[wl + 16 * e] = n[e];
         }
         __syncwarp();
         // Blocked layout for the row sums: lane l sums entries 4l .. 4l+3, one segmented scan over the 32 lane tails
-        const double2 ma = *reinterpret_cast<const double2*>(s_n + 4 * lane);
-        const double2 mb = *reinterpret_cast<const double2*>(s_n + 4 * lane + 2);
+        const double2 ma = *reinterpret_cast<const double2*>(s_n + 2 * lane);
+        const double2 mb = *reinterpret_cast<const double2*>(s_n + 72 + 2 * lane);
         const double m[4] = {ma.x, ma.y, mb.x, mb.y};
         const unsigned w_lo = F[wsel];
         const unsigned w_hi = (wsel < 3) ? F[(wsel + 1) & 3] : 1u;          // position 128 counts as a read start
@@ -314,7 +305,7 @@ k_tiles(const TileArgs a) {
             nb += __popc(F[e]);
             if ((32 * e + lane) < end) {
                 const double c = n[e] * s_g[lr];
-                if (MODE == TILE_FUSED) { if (c != 0.0) atomicAdd(my + cc[e], c); }
+                if (MODE == TILE_FUSED) atomicAdd(my + cc[e], c);     // adding an exact 0.0 (unique reads) is harmless
                 if (MODE == TILE_Z) a.z_out[base + 32 * e + lane] = c;
                 if (MODE == TILE_LNL) {
                     if (c != 0.0) {

@@ -128,6 +128,8 @@ int tsc_get_em_device_ms(tsc_handle* h, float* ms_out);
  * Does not change pi/theta or the EM state.
  */
 int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float* mean_ms);
+/* Diagnostic: host-side wall time of the stages of tsc_create, "stage=ms;stage=ms;..." (valid until tsc_destroy) */
+const char* tsc_create_laps(tsc_handle* h);
 /* All-reduce n (<= 8) host doubles over every shard of every process of this handle's communicator (op 0 = sum,
  * 1 = max); with n_procs == 1 and one device it is the identity.  Lets multi-process drivers agree on timings and
  * synchronise without a second communication library. */

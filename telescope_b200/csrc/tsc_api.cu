@@ -143,6 +143,7 @@ struct tsc_handle {
     std::vector<long long> rowmap;        // compacted read -> caller's read index (empty when no empty reads)
     std::vector<int> perm, inv;           // perm[original] = internal; inv[internal] = original
     int n_dup_loci = 0;                   // loci whose column duplicates an earlier locus's
+    std::string create_laps;              // host-side construction laps ("stage=ms;")
     Consts consts{};
     std::vector<double> pisum0_host;
     bool em_done = false;
@@ -279,13 +280,15 @@ extern "C" void tsc_destroy(tsc_handle* h) {
 
 // ------------------------------------------------------------------------------------------------- create
 struct StageTimer {
-    bool on;
+    bool on;                 // TELESCOPE_B200_TIMING: print laps and synchronise at lap boundaries
+    std::string* log;        // always: host-side laps, no extra synchronisation
     std::chrono::steady_clock::time_point t0;
-    StageTimer() : on(getenv("TELESCOPE_B200_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    explicit StageTimer(std::string* l) : on(getenv("TELESCOPE_B200_TIMING") != nullptr), log(l), t0(std::chrono::steady_clock::now()) {}
     void lap(const char* what) {
-        if (!on) return;
         auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[tsc_create] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        if (on) fprintf(stderr, "[tsc_create] %-28s %8.1f ms\n", what, ms);
+        if (log) { char buf[96]; snprintf(buf, sizeof buf, "%s=%.1f;", what, ms); *log += buf; }
         t0 = t1;
     }
 };
@@ -316,7 +319,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         if (d < 0 || d >= ndev) return fail(TSC_ERR_ARG, "device id " + std::to_string(d) + " not present");
     }
 
-    StageTimer tm;
+    StageTimer tm(&h->create_laps);
     // ---- read pointers.  Fast path: the caller's array is used as is (validated and rebased on the device).
     // Matrices with empty reads take the slow path: the reads are compacted on the host first.
     auto ip_at = [&](int64_t i) -> long long {
@@ -793,6 +796,8 @@ extern "C" void* tsc_pinned_alloc(uint64_t bytes) {
     return p;
 }
 extern "C" void tsc_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" const char* tsc_create_laps(tsc_handle* h) { return h ? h->create_laps.c_str() : ""; }
 
 extern "C" int tsc_allreduce_f64(tsc_handle* h, double* inout, int32_t n, int32_t op) {
     if (!h || !inout || n <= 0 || n > 8 || (op != 0 && op != 1)) return fail(TSC_ERR_ARG, "bad argument");

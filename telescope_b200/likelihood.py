@@ -100,12 +100,16 @@ class TelescopeLikelihood(object):
         cfg.smem_table_cols = smem_table_cols
         cfg.permute_columns = 1 if permute_columns else 0
         h = C.c_void_p()
+        import time as _time
+        _t0 = _time.perf_counter()
         _abi.check(self._lib.tsc_create(
             C.byref(h), C.byref(cfg), self.N, self.K, int(indices.size),
             indptr.ctypes.data_as(C.c_void_p), indptr.dtype.itemsize, _abi._p(indices, C.c_int32),
             _abi._p(raw, C.c_uint16), _abi._p(self._lut, C.c_double), int(self._lut.size),
             float(self.pi_prior), float(self.theta_prior)))
         self._h = h
+        self.create_seconds = _time.perf_counter() - _t0          # diagnostics: time inside tsc_create
+        self.create_laps = self._lib.tsc_create_laps(self._h).decode()
 
         sc = np.zeros(5)
         pisum0 = np.zeros(self.K)

@@ -263,3 +263,45 @@ def test_bad_inputs_are_rejected():
         tl.reassign("exclude")                            # self.z is None before em()
     assert tl.reassign("exclude", initial=True).shape == good.shape
     tl.close()
+
+
+def test_config2_full_size_against_oracle():
+    """BASELINE.json config 2: 1 M reads x 5 k loci, avg 10 alignments/read (1e7 entries), straight against the oracle."""
+    m = _matrix(N=1_000_000, K=5000, avg=10, skew=False, seed=1002)
+    opts = Opts(max_iter=6, em_epsilon=-1)
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    tl.em(); o.em()
+    assert tl.n_iter == o.n_iter == 6
+    assert rel_err(tl.pi, o.pi) < RTOL and rel_err(tl.theta, o.theta) < RTOL and rel_err(tl.diffs, o.diffs) < RTOL
+    assert abs(tl.lnl - o.lnl) <= RTOL * abs(o.lnl)
+    for method, initial in [("exclude", False), ("exclude", True), ("unique", False), ("all", True)]:
+        assert np.array_equal(tl.reassign_colsum(method, 0.9, initial), o.reassign_colsum(method, 0.9, initial))
+    tl.close()
+
+
+def test_config3_size_independent_properties():
+    """BASELINE.json config 3 size (10 M reads x 15 k loci, ~2e8 entries): invariants that need no CPU EM.
+      * pi and theta are proportions (pi_prior = 0): each sums to 1
+      * every ambiguous read's posterior row sums to 1 -> sum_j thetasum_j = ambig_wt, i.e. sum(theta) = 1 exactly as above
+      * reassign('all', initial) counts the stored entries per locus, reassign('unique') the single-hit reads (integers,
+        independent of EM) -> compared with numpy bincounts
+      * the rows kernel and the flat-tile kernel agree
+    """
+    N, K = 10_000_000, 15000
+    m = _matrix(N=N, K=K, avg=20, skew=False, seed=1003)
+    opts = Opts(max_iter=5, em_epsilon=-1)
+    a = _tl(m, opts, kernel="tiles")
+    a.em()
+    assert abs(a.pi.sum() - 1.0) < 1e-9 and abs(a.theta.sum() - 1.0) < 1e-9
+    assert a.n_iter == 5 and np.all(np.diff(a.diffs) < 0), "diff_est shrinks from the uniform start"
+    lens = np.diff(m.indptr)
+    assert np.array_equal(a.reassign_colsum("all", initial=True), np.bincount(m.indices, minlength=K).astype(np.uint64))
+    uniq_rows = np.flatnonzero(lens == 1)
+    assert np.array_equal(a.reassign_colsum("unique"), np.bincount(m.indices[m.indptr[uniq_rows]], minlength=K).astype(np.uint64))
+    ex = a.reassign_colsum("exclude")
+    assert ex.sum() <= N and ex.sum() >= int(0.9 * N)
+    b = _tl(m, opts, kernel="rows")
+    b.em()
+    assert rel_err(a.pi, b.pi) < 1e-9 and abs(a.lnl - b.lnl) <= 1e-10 * abs(a.lnl)
+    assert np.array_equal(ex, b.reassign_colsum("exclude"))
+    a.close(); b.close()

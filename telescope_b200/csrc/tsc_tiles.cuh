@@ -209,9 +209,40 @@ k_tiles(const TileArgs a) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(tiles + tn));
 
         if (end == 0) {
-            // ---- long read (always ambiguous): the whole warp walks it twice
+            // ---- long read (more than 128 entries, always ambiguous): the whole warp takes it
             const long long len = ((long long)F[0]) | ((long long)F[1] << 32);
             const long long hi = base + len;
+            if (len <= 256) {
+                // up to 8 entries per lane stay in registers: one pass over memory, like a regular tile
+                int c8[8];
+                double n8[8];
+                double sum = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const long long p = base + lane + 32 * i;        // reads past the end hit padding / the next tile
+                    c8[i] = ld_stream(col + p);
+                    n8[i] = ld_stream(q + p);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    n8[i] = (base + lane + 32 * i < hi) ? n8[i] * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, c8[i]) : 0.0;
+                    sum += n8[i];
+                }
+                sum = group_sum<32>(sum, 0xffffffffu);
+                const double g = (MODE == TILE_FUSED) ? a.wy[row0] * recip0(sum) : recip0(sum);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const long long p = base + lane + 32 * i;
+                    if (p < hi) {
+                        const double c = n8[i] * g;
+                        if (MODE == TILE_FUSED) atomicAdd(my + c8[i], c);
+                        if (MODE == TILE_Z) __stcs(a.z_out + p, c);
+                        if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p(__ldg(q + p) * __ldg(a.inner_amb + c8[i])); }
+                    }
+                }
+                continue;
+            }
+            // longer still: two passes over the read
             double sum = 0;
             for (long long p = base + lane; p < hi; p += 32)
                 sum += ld_stream(q + p) * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, ld_stream(col + p));
@@ -223,7 +254,7 @@ k_tiles(const TileArgs a) {
                     const double qv = q[p];
                     const double c = (qv * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, cc)) * g;
                     if (MODE == TILE_FUSED) { if (c != 0.0) atomicAdd(my + cc, c); }
-                    if (MODE == TILE_Z) a.z_out[p] = c;
+                    if (MODE == TILE_Z) __stcs(a.z_out + p, c);
                     if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p(qv * __ldg(a.inner_amb + cc)); }
                 }
             }
@@ -306,7 +337,7 @@ k_tiles(const TileArgs a) {
             if ((32 * e + lane) < end) {
                 const double c = n[e] * s_g[lr];
                 if (MODE == TILE_FUSED) atomicAdd(my + cc[e], c);     // adding an exact 0.0 (unique reads) is harmless
-                if (MODE == TILE_Z) a.z_out[base + 32 * e + lane] = c;
+                if (MODE == TILE_Z) __stcs(a.z_out + base + 32 * e + lane, c);      // written once, never re-read here
                 if (MODE == TILE_LNL) {
                     if (c != 0.0) {
                         const unsigned nxt = (e < 3) ? F[(e + 1) & 3] : 1u;

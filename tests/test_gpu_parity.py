@@ -305,3 +305,30 @@ def test_config3_size_independent_properties():
     assert rel_err(a.pi, b.pi) < 1e-9 and abs(a.lnl - b.lnl) <= 1e-10 * abs(a.lnl)
     assert np.array_equal(ex, b.reassign_colsum("exclude"))
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("kernel", ["tiles", "rows"])
+def test_long_reads_every_path(kernel):
+    """Reads of 129..256 entries (single-pass long path), > 256 (two-pass path), exactly 128 (a full regular tile) and
+    short ones, interleaved, against the oracle -- fused kernel, posterior export, log-likelihood and reassignment."""
+    K = 900
+    rng = np.random.default_rng(81)
+    lens = [128, 129, 1, 200, 5, 256, 257, 2, 400, 128, 127, 3, 700, 64, 64, 1, 130, 899] * 6
+    rows = [np.sort(rng.choice(K, n, replace=False)) for n in lens]
+    indptr = np.cumsum([0] + lens)
+    indices = np.concatenate(rows).astype(np.int32)
+    raw = (150 + rng.integers(0, 60, indices.size)).astype(np.uint16)
+    m = sp.csr_matrix((raw, indices, indptr), shape=(len(lens), K))
+    opts = Opts(max_iter=6)
+    tl, o = _tl(m, opts, kernel=kernel), _oracle(m, opts)
+    tl.em(); o.em()
+    assert tl.n_iter == o.n_iter
+    assert rel_err(tl.pi, o.pi) < TIGHT and rel_err(tl.theta, o.theta) < TIGHT
+    assert abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
+    assert rel_err(_dense_z(tl.z, m), o.z) < TIGHT
+    assert rel_err(_dense_z(tl.reassign("all", initial=True).astype(np.float64).multiply(tl.Q.norm(1)), m), o.initial_z()) < 1e-12
+    for method in ("exclude", "unique", "all"):
+        assert np.array_equal(tl.reassign_colsum(method), o.reassign_colsum(method))
+    tl.em(use_likelihood=True); o.em(use_likelihood=True)
+    assert tl.n_iter == o.n_iter and abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
+    tl.close()

@@ -215,6 +215,21 @@ static int launch_rows(int G, F&& f) {
 
 static Csr csr_of(const Shard& s) { return Csr{s.indptr, s.col, s.q, s.n_rows}; }
 
+// ------------------------------------------------------------------------------------------------- tile launches
+template <int MODE>
+static void launch_tiles(const Shard& s, const TileArgs& a, bool smem_tab) {
+    const size_t scratch = sizeof(double) * kTileWarps * kScratch;
+    const bool long8 = s.n_long * 200 > s.n_tiles;      // > 0.5 % of the tiles are long reads
+    if (MODE == TILE_FUSED && smem_tab) {
+        if (long8) k_tiles<MODE, true, true><<<s.grid_tiles, kTileThreads, s.smem_tiles, s.stream>>>(a);
+        else k_tiles<MODE, true, false><<<s.grid_tiles, kTileThreads, s.smem_tiles, s.stream>>>(a);
+    } else {
+        if (long8) k_tiles<MODE, false, true><<<s.grid_tiles, kTileThreads, scratch, s.stream>>>(a);
+        else k_tiles<MODE, false, false><<<s.grid_tiles, kTileThreads, scratch, s.stream>>>(a);
+    }
+}
+
+
 // ------------------------------------------------------------------------------------------------- small API
 extern "C" int tsc_abi_version(void) { return TSC_ABI_VERSION; }
 extern "C" const char* tsc_last_error(void) { return g_err.c_str(); }
@@ -658,16 +673,21 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
             const int fit = (int)((max_optin - scratch - 1024) / sizeof(double));
             s.s_cols = std::min(want, std::max(fit, 0));
             s.smem_tiles = scratch + sizeof(double) * s.s_cols;
-            CU(cudaFuncSetAttribute(k_tiles<TILE_FUSED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(s.smem_tiles, scratch)));
-            CU(cudaFuncSetAttribute(k_tiles<TILE_FUSED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
-            CU(cudaFuncSetAttribute(k_tiles<TILE_Z, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
-            CU(cudaFuncSetAttribute(k_tiles<TILE_LNL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+            const int big = (int)std::max(s.smem_tiles, scratch);
+            CU(cudaFuncSetAttribute(k_tiles<TILE_FUSED, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            CU(cudaFuncSetAttribute(k_tiles<TILE_FUSED, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            CU(cudaFuncSetAttribute(k_tiles<TILE_FUSED, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+            CU(cudaFuncSetAttribute(k_tiles<TILE_FUSED, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+            CU(cudaFuncSetAttribute(k_tiles<TILE_Z, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+            CU(cudaFuncSetAttribute(k_tiles<TILE_Z, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+            CU(cudaFuncSetAttribute(k_tiles<TILE_LNL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
+            CU(cudaFuncSetAttribute(k_tiles<TILE_LNL, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch));
             if (s.s_cols > 0) {
                 h->smem_tab = true;
                 s.grid_tiles = s.n_sm;
             } else {
                 int per_sm = 0;
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiles<TILE_FUSED, false>, kTileThreads, scratch));
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiles<TILE_FUSED, false, true>, kTileThreads, scratch));
                 s.grid_tiles = s.n_sm * std::max(per_sm, 1);
             }
         }
@@ -823,7 +843,6 @@ extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float
     if (!h || !mean_ms || reps <= 0) return fail(TSC_ERR_ARG, "bad argument");
     Shard& s = h->shards[0];
     CU(cudaSetDevice(s.dev));
-    const size_t scratch = sizeof(double) * kTileWarps * kScratch;
     double* zd = nullptr;
     if (pass_id == 1) CU(cudaMalloc(&zd, sizeof(double) * std::max<long long>(s.nnz, 1)));
     cudaEvent_t e0, e1;
@@ -839,15 +858,15 @@ extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float
         switch (pass_id) {
             case 0:
                 a.wy = s.wy; a.tab_amb = s.pt; a.acc = s.acc;
-                k_tiles<TILE_FUSED, false><<<s.grid_tiles, kTileThreads, scratch, s.stream>>>(a);
+                launch_tiles<TILE_FUSED>(s, a, false);
                 break;
             case 1:
                 a.tab_amb = ta; a.tab_uni = tu; a.z_out = zd;
-                k_tiles<TILE_Z, false><<<s.grid_tiles, kTileThreads, scratch, s.stream>>>(a);
+                launch_tiles<TILE_Z>(s, a, false);
                 break;
             case 2:
                 a.tab_amb = ta; a.tab_uni = tu; a.inner_amb = s.pt; a.inner_uni = s.pi; a.partials = s.partials;
-                k_tiles<TILE_LNL, false><<<s.grid_tiles, kTileThreads, scratch, s.stream>>>(a);
+                launch_tiles<TILE_LNL>(s, a, false);
                 break;
             case 3: {
                 ReassignArgs g{TSC_EXCLUDE, 0.9, nullptr, nullptr, s.colsum, nullptr};
@@ -893,8 +912,7 @@ static int launch_fused(tsc_handle* h, Shard& s) {
         TileArgs a{};
         a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.wy = s.wy; a.tab_amb = s.pt;
         a.acc = s.acc; a.K = h->K; a.R = h->R; a.s_cols = s.s_cols; a.st = s.st;
-        if (s.s_cols > 0) k_tiles<TILE_FUSED, true><<<s.grid_tiles, kTileThreads, s.smem_tiles, s.stream>>>(a);
-        else k_tiles<TILE_FUSED, false><<<s.grid_tiles, kTileThreads, sizeof(double) * kTileWarps * kScratch, s.stream>>>(a);
+        launch_tiles<TILE_FUSED>(s, a, s.s_cols > 0);
     }
     LAUNCH(h);
     CU(cudaGetLastError());
@@ -915,7 +933,7 @@ static int launch_lnl(tsc_handle* h, const double* (*zin_of)(Shard&), bool from_
             a.tab_amb = s.pt_prev; a.tab_uni = s.pi_prev; a.inner_amb = ia(s); a.inner_uni = iu(s);
             a.K = h->K; a.st = st; a.partials = s.partials;
             nparts = s.grid_tiles;
-            k_tiles<TILE_LNL, false><<<s.grid_tiles, kTileThreads, sizeof(double) * kTileWarps * kScratch, s.stream>>>(a);
+            launch_tiles<TILE_LNL>(s, a, false);
         } else {
             launch_rows(h->G, [&](auto g) {
                 k_lnl_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(
@@ -1072,7 +1090,7 @@ static int z_to_host(tsc_handle* h, const double* tab_amb_sel, int which, double
             TileArgs a{};
             a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.tab_amb = ta; a.tab_uni = tu;
             a.K = h->K; a.z_out = zd;
-            k_tiles<TILE_Z, false><<<s.grid_tiles, kTileThreads, sizeof(double) * kTileWarps * kScratch, s.stream>>>(a);
+            launch_tiles<TILE_Z>(s, a, false);
         } else {
             launch_rows(h->G, [&](auto g) {
                 k_estep_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, zd);

@@ -165,65 +165,10 @@ struct TileArgs {
     double* partials;          // LNL: one partial sum per block
 };
 
-// Reads longer than a tile (always ambiguous).  Kept out of line so that its register needs (8 entries per lane) do
-// not shape the allocation of the regular-tile loop; the whole warp calls it together.
-template <int MODE, bool SMEM_TAB>
-__device__ __noinline__ double long_read(const double* __restrict__ q, const int* __restrict__ col,
-                                         const double* __restrict__ pt, int s_cols, const double* __restrict__ wy,
-                                         double* __restrict__ z_out, const double* __restrict__ inner_amb,
-                                         long long base, long long len, int row0, int lane, const double* s_tab, double* my) {
-    double lnl_local = 0.0;
-    const long long hi = base + len;
-    if (len <= 256) {
-        // up to 8 entries per lane stay in registers: one pass over memory, like a regular tile
-        int c8[8];
-        double n8[8];
-        double sum = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const long long p = base + lane + 32 * i;        // reads past the end hit padding / the next tile
-            c8[i] = ld_stream(col + p);
-            n8[i] = ld_stream(q + p);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            n8[i] = (base + lane + 32 * i < hi) ? n8[i] * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, c8[i]) : 0.0;
-            sum += n8[i];
-        }
-        sum = group_sum<32>(sum, 0xffffffffu);
-        const double g = (MODE == TILE_FUSED) ? wy[row0] * recip0(sum) : recip0(sum);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const long long p = base + lane + 32 * i;
-            if (p < hi) {
-                const double c = n8[i] * g;
-                if (MODE == TILE_FUSED) atomicAdd(my + c8[i], c);
-                if (MODE == TILE_Z) __stcs(z_out + p, c);
-                if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p(__ldg(q + p) * __ldg(inner_amb + c8[i])); }
-            }
-        }
-        return lnl_local;
-    }
-    // longer still: two passes over the read
-    double sum = 0;
-    for (long long p = base + lane; p < hi; p += 32)
-        sum += ld_stream(q + p) * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, ld_stream(col + p));
-    sum = group_sum<32>(sum, 0xffffffffu);
-    const double g = (MODE == TILE_FUSED) ? wy[row0] * recip0(sum) : recip0(sum);
-    if (MODE != TILE_FUSED || g != 0.0) {
-        for (long long p = base + lane; p < hi; p += 32) {
-            const int cc = col[p];
-            const double qv = q[p];
-            const double c = (qv * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, cc)) * g;
-            if (MODE == TILE_FUSED) { if (c != 0.0) atomicAdd(my + cc, c); }
-            if (MODE == TILE_Z) __stcs(z_out + p, c);
-            if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p(qv * __ldg(inner_amb + cc)); }
-        }
-    }
-    return lnl_local;
-}
-
-template <int MODE, bool SMEM_TAB>
+// LONG8: compile the single-pass path for reads of 129..256 entries (8 per lane in registers).  It wins big when
+// such reads are common (Zipf rows: 140 -> 192 EM iterations/s) and costs ~2 % when there are none (its registers
+// shape the allocation of the regular loop), so the host instantiates it only for shards that have long reads.
+template <int MODE, bool SMEM_TAB, bool LONG8>
 __global__ void __launch_bounds__(kTileThreads, TSC_TILE_MINBLOCKS)
 k_tiles(const TileArgs a) {
     extern __shared__ double s_dyn[];
@@ -266,9 +211,56 @@ k_tiles(const TileArgs a) {
         const long long tn = (t + nwarps < n_tiles) ? t + nwarps : t;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(tiles + tn));
 
-        if (end == 0) {   // long read: its own tile, handled out of line
+        if (end == 0) {
+            // ---- long read (more than 128 entries, always ambiguous): the whole warp takes it
             const long long len = ((long long)F[0]) | ((long long)F[1] << 32);
-            lnl_local += long_read<MODE, SMEM_TAB>(q, col, pt, s_cols, a.wy, a.z_out, a.inner_amb, base, len, row0, lane, s_tab, my);
+            const long long hi = base + len;
+            if (LONG8 && len <= 256) {
+                // up to 8 entries per lane stay in registers: one pass over memory, like a regular tile
+                int c8[8];
+                double n8[8];
+                double sum = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const long long p = base + lane + 32 * i;        // reads past the end hit padding / the next tile
+                    c8[i] = ld_stream(col + p);
+                    n8[i] = ld_stream(q + p);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    n8[i] = (base + lane + 32 * i < hi) ? n8[i] * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, c8[i]) : 0.0;
+                    sum += n8[i];
+                }
+                sum = group_sum<32>(sum, 0xffffffffu);
+                const double g = (MODE == TILE_FUSED) ? a.wy[row0] * recip0(sum) : recip0(sum);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const long long p = base + lane + 32 * i;
+                    if (p < hi) {
+                        const double c = n8[i] * g;
+                        if (MODE == TILE_FUSED) atomicAdd(my + c8[i], c);
+                        if (MODE == TILE_Z) __stcs(a.z_out + p, c);
+                        if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p(__ldg(q + p) * __ldg(a.inner_amb + c8[i])); }
+                    }
+                }
+                continue;
+            }
+            // longer still: two passes over the read
+            double sum = 0;
+            for (long long p = base + lane; p < hi; p += 32)
+                sum += ld_stream(q + p) * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, ld_stream(col + p));
+            sum = group_sum<32>(sum, 0xffffffffu);
+            const double g = (MODE == TILE_FUSED) ? a.wy[row0] * recip0(sum) : recip0(sum);
+            if (MODE != TILE_FUSED || g != 0.0) {
+                for (long long p = base + lane; p < hi; p += 32) {
+                    const int cc = col[p];
+                    const double qv = q[p];
+                    const double c = (qv * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, cc)) * g;
+                    if (MODE == TILE_FUSED) { if (c != 0.0) atomicAdd(my + cc, c); }
+                    if (MODE == TILE_Z) __stcs(a.z_out + p, c);
+                    if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p(qv * __ldg(a.inner_amb + cc)); }
+                }
+            }
             continue;
         }
 

@@ -65,8 +65,9 @@ typedef struct {
     const void* nccl_id;       /* 128-byte id from tsc_nccl_unique_id() of rank 0; required iff n_procs > 1 */
     int32_t kernel;            /* tsc_kernel */
     int32_t replicas;          /* copies of the per-locus accumulator in L2 (0 = auto) */
-    int32_t smem_table_cols;   /* loci whose pi*theta entry is staged in shared memory (-1 = auto) */
-    int32_t smem_acc_cols;     /* loci accumulated in shared memory before flushing (-1 = auto) */
+    int32_t smem_table_cols;   /* loci whose pi*theta entry is staged in shared memory (-1 = auto = 0: the L1/L2
+                                  gather measured faster, profiles/r1_microbench_scatter_gather.log) */
+    int32_t smem_acc_cols;     /* reserved (shared-memory fp64 atomics are CAS loops on sm_100a; not used) */
     int32_t permute_columns;   /* 1 = renumber loci by descending entry count internally, 0 = keep the caller's
                                   numbering (default: neighbouring loci share sectors, which the scatter-add likes) */
     int32_t reserved[6];

@@ -183,13 +183,6 @@ __global__ void k_mul(const double* __restrict__ a, const double* __restrict__ b
     if (i < n) out[i] = a[i] * b[i];
 }
 
-// out[perm[j]] = in[j] (to internal numbering) or out[j] = in[perm[j]] (back)
-__global__ void k_permute(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ perm,
-                          int n, int to_internal) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) { if (to_internal) out[perm[j]] = in[j]; else out[j] = in[perm[j]]; }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // per-iteration K-length kernels
 // ---------------------------------------------------------------------------------------------------------------

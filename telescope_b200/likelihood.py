@@ -22,6 +22,18 @@ from .sparse_plus import draw_picks
 _INT_DTYPE = {"exclude": np.int8, "choose": np.int8, "unique": np.uint8, "all": np.uint8}
 
 
+def _nccl_env_defaults():
+    """The only collective on this path is a latency-bound all-reduce of K doubles, so communicator SETUP cost is
+    what matters: without NVLS (multicast) setup and with two channels ncclCommInitRank takes about half as long on
+    an 8 x B200 box and the per-iteration time is unchanged (profiles/r1_nccl_init.md).  Only variables the user has
+    not set are touched; TELESCOPE_B200_NCCL_TUNE=0 leaves NCCL alone."""
+    import os
+    if os.environ.get("TELESCOPE_B200_NCCL_TUNE", "1") == "0":
+        return
+    os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+    os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
+
+
 class DistInfo(object):
     """How this process takes part in a multi-process run (one process per GPU, e.g. under torchrun)."""
 
@@ -92,6 +104,7 @@ class TelescopeLikelihood(object):
             self._nccl_id = C.create_string_buffer(dist.nccl_id, 128)
             cfg.nccl_id = C.cast(self._nccl_id, C.c_void_p)
         if len(devices) > 1 or (dist is not None and dist.n_procs > 1):
+            _nccl_env_defaults()
             path = _abi.find_nccl()
             if path:
                 self._lib.tsc_set_nccl_path(path.encode())

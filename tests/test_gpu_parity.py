@@ -332,3 +332,21 @@ def test_long_reads_every_path(kernel):
     tl.em(use_likelihood=True); o.em(use_likelihood=True)
     assert tl.n_iter == o.n_iter and abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
     tl.close()
+
+
+@pytest.mark.parametrize("kw", [dict(permute_columns=True), dict(smem_table_cols=64), dict(smem_table_cols=10 ** 6),
+                                dict(replicas=1), dict(replicas=64, permute_columns=True, smem_table_cols=100)])
+def test_non_default_device_options_give_the_same_answer(kw):
+    """Locus renumbering by frequency, a shared-memory copy of (part of) the pi*theta table and the replica count are
+    tuning knobs only."""
+    m = _matrix(N=20000, K=1500, avg=20, skew=True, seed=91)
+    opts = Opts(max_iter=10)
+    tl, o = _tl(m, opts, **kw), _oracle(m, opts)
+    tl.em(); o.em()
+    assert tl.n_iter == o.n_iter
+    assert rel_err(tl.pi, o.pi) < TIGHT and rel_err(tl.theta, o.theta) < TIGHT
+    assert abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
+    assert rel_err(np.asarray(tl._pisum0).ravel(), o.pisum0) < 1e-12
+    for method, initial in [("exclude", False), ("exclude", True), ("all", True)]:
+        assert np.array_equal(tl.reassign_colsum(method, 0.9, initial), o.reassign_colsum(method, 0.9, initial))
+    tl.close()

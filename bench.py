@@ -133,7 +133,7 @@ class ClockSampler(object):
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -284,13 +284,14 @@ def main():
     c_e2e = tl.counters()
     lnl_first = tl.lnl
 
-    # ---- device-resident: W warm-up iterations, then exactly K timed ones
+    # ---- device-resident: W warm-up iterations, then exactly K timed ones.  Clocks are sampled from the warm-up to
+    # the end of the extra kernel timings below (the GPU is under the same kind of load throughout).
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     if W > 0:
         tl.max_iter = W
         tl.em()
     tl.max_iter = K
     c0 = tl.counters()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     t0 = time.perf_counter()
     tl.em()
@@ -298,7 +299,6 @@ def main():
     dev_ms = max_over_ranks(tl.em_device_ms())
     wall = max_over_ranks(wall)
     barrier()
-    clocks = sampler.stop() if sampler else None
     c1 = tl.counters()
     kms = tl.kernel_times_ms()
     kern_ms = max_over_ranks(float(np.mean(kms)) if len(kms) else float("nan"))
@@ -311,6 +311,7 @@ def main():
             passes[name] = max_over_ranks(tl.time_pass(name, 3))
         except Exception as exc:      # e.g. not enough memory for the 8 B/entry z buffer
             passes[name] = None
+    clocks = sampler.stop() if sampler else None
     value = K / (dev_ms * 1e-3)
     peak, peak_src = hbm_peak()
     rows_local = hi - lo

@@ -270,7 +270,9 @@ def main():
     warm = TelescopeLikelihood(sp.csr_matrix((wr, wx, wi), shape=(4096, 64)), Opts(2), devices=[local_rank])
     warm.em()
     warm.close()
-    # ---- e2e: the whole job through the public class, host buffers in, parameters out
+    # ---- e2e: the whole job through the public class, host buffers in, parameters out.  All ranks start together
+    # (no communicator exists yet, so the barrier goes through the launcher-shared temp files).
+    tsc_dist.file_barrier("e2e")
     t0 = time.perf_counter()
     tl = TelescopeLikelihood(m, Opts(K), **kw)
     live["tl"] = tl

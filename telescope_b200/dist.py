@@ -53,10 +53,27 @@ def rendezvous(timeout=600.0):
     return DistInfo(world, rank, ident)
 
 
+def file_barrier(tag, timeout=600.0):
+    """Barrier for the ranks of one launch before any communicator exists (same shared-parent file scheme)."""
+    rank, world, _ = env_world()
+    if world <= 1:
+        return
+    base = "%s.%s." % (_rdzv_path(), tag)
+    with open(base + str(rank), "w"):
+        pass
+    t0 = time.time()
+    while not all(os.path.exists(base + str(r)) for r in range(world)):
+        if time.time() - t0 > timeout:
+            raise RuntimeError("rank %d: barrier %r timed out" % (rank, tag))
+        time.sleep(0.005)
+
+
 def cleanup():
     rank, world, _ = env_world()
     if world > 1 and rank == 0:
-        try:
-            os.unlink(_rdzv_path())
-        except OSError:
-            pass
+        import glob
+        for f in glob.glob(_rdzv_path() + "*"):
+            try:
+                os.unlink(f)
+            except OSError:
+                pass

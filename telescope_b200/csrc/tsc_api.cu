@@ -161,8 +161,7 @@ static inline int grid_for(long long work, int threads, int cap) {
     return (int)std::max<long long>(1, std::min<long long>(b, cap));
 }
 
-static int allreduce(tsc_handle* h, size_t off_bytes_unused, void* (*ptr_of)(Shard&), size_t count, ncclDataType_t dt, ncclRedOp_t op) {
-    (void)off_bytes_unused;
+static int allreduce(tsc_handle* h, void* (*ptr_of)(Shard&), size_t count, ncclDataType_t dt, ncclRedOp_t op) {
     if (h->world == 1) return TSC_OK;
     NC(g_nccl.GroupStart());
     for (auto& s : h->shards) {
@@ -175,7 +174,7 @@ static int allreduce(tsc_handle* h, size_t off_bytes_unused, void* (*ptr_of)(Sha
 }
 #define ALLREDUCE(h, member_expr, count, dt, op)                                                   \
     do {                                                                                           \
-        int rc_ = allreduce((h), 0, [](Shard& s) -> void* { return (void*)(member_expr); }, (count), (dt), (op)); \
+        int rc_ = allreduce((h), [](Shard& s) -> void* { return (void*)(member_expr); }, (count), (dt), (op)); \
         if (rc_) return rc_;                                                                       \
     } while (0)
 
@@ -308,13 +307,48 @@ struct StageTimer {
     }
 };
 
-static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user, int32_t n_cols, int64_t nnz,
-                       const void* indptr, int32_t indptr_bytes, const int32_t* indices, const uint16_t* raw,
-                       const double* q_lut, int32_t lut_len, double pi_prior, double theta_prior) {
-    const int K = n_cols;
-    h->K = K;
-    h->n_rows_user = n_rows_user;
-    h->nnz = nnz;
+struct CreateInput {
+    int64_t n_rows_user;
+    int32_t n_cols;
+    int64_t nnz;
+    const void* indptr;
+    int32_t indptr_bytes;
+    const int32_t* indices;
+    const uint16_t* raw;
+    const double* q_lut;
+    int32_t lut_len;
+    double pi_prior, theta_prior;
+    long long ip_at(int64_t i) const {
+        return indptr_bytes == 4 ? (long long)((const int32_t*)indptr)[i] : (long long)((const int64_t*)indptr)[i];
+    }
+};
+
+constexpr int kNeedsCompaction = -1;    // internal: empty reads were found on the device, retry with compacted reads
+
+// Reads with no entries are dropped on the host (slow path): ip becomes the compacted read pointers, h->rowmap the
+// compacted -> caller read index.
+static int compact_on_host(tsc_handle* h, const CreateInput& in, std::vector<long long>& ip) {
+    std::vector<long long> full((size_t)in.n_rows_user + 1);
+    for (int64_t i = 0; i <= in.n_rows_user; ++i) full[i] = in.ip_at(i);
+    for (int64_t i = 0; i < in.n_rows_user; ++i)
+        if (full[i + 1] < full[i]) return fail(TSC_ERR_ARG, "indptr is not non-decreasing");
+    h->rowmap.clear();
+    h->rowmap.reserve(in.n_rows_user);
+    ip.clear();
+    ip.reserve(in.n_rows_user + 1);
+    ip.push_back(0);
+    for (int64_t i = 0; i < in.n_rows_user; ++i)
+        if (full[i + 1] > full[i]) { h->rowmap.push_back(i); ip.push_back(full[i + 1]); }
+    return TSC_OK;
+}
+
+static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInput& in, const std::vector<long long>* ip_compact,
+                          StageTimer& tm);
+
+static int create_impl(tsc_handle* h, const tsc_config& cfg, const CreateInput& in) {
+    h->K = in.n_cols;
+    h->n_rows_user = in.n_rows_user;
+    h->nnz = in.nnz;
     h->n_procs = std::max(1, cfg.n_procs);
     h->proc_rank = cfg.proc_rank;
     const int n_local = std::max(1, cfg.n_local_devices);
@@ -333,38 +367,43 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
         const int d = cfg.device_ids ? cfg.device_ids[i] : i;
         if (d < 0 || d >= ndev) return fail(TSC_ERR_ARG, "device id " + std::to_string(d) + " not present");
     }
+    if (in.ip_at(0) != 0 || in.ip_at(in.n_rows_user) != in.nnz)
+        return fail(TSC_ERR_ARG, "indptr[0] must be 0 and indptr[n_rows] must be nnz");
 
     StageTimer tm(&h->create_laps);
-    // ---- read pointers.  Fast path: the caller's array is used as is (validated and rebased on the device).
-    // Matrices with empty reads take the slow path: the reads are compacted on the host first.
-    auto ip_at = [&](int64_t i) -> long long {
-        return indptr_bytes == 4 ? (long long)((const int32_t*)indptr)[i] : (long long)((const int64_t*)indptr)[i];
-    };
-    if (ip_at(0) != 0 || ip_at(n_rows_user) != nnz) return fail(TSC_ERR_ARG, "indptr[0] must be 0 and indptr[n_rows] must be nnz");
-    std::vector<long long> ip;          // only filled on the slow path
-    auto compact_on_host = [&]() -> int {
-        std::vector<long long> full((size_t)n_rows_user + 1);
-        for (int64_t i = 0; i <= n_rows_user; ++i) full[i] = ip_at(i);
-        for (int64_t i = 0; i < n_rows_user; ++i)
-            if (full[i + 1] < full[i]) return fail(TSC_ERR_ARG, "indptr is not non-decreasing");
-        h->rowmap.clear();
-        h->rowmap.reserve(n_rows_user);
-        ip.clear();
-        ip.reserve(n_rows_user + 1);
-        ip.push_back(0);
-        for (int64_t i = 0; i < n_rows_user; ++i)
-            if (full[i + 1] > full[i]) { h->rowmap.push_back(i); ip.push_back(full[i + 1]); }
-        return TSC_OK;
-    };
+    // Fast path: the caller's read pointers are used as they are (validated and rebased on the device).  Matrices
+    // with empty reads take the slow path: tiny ones are checked here, large ones are detected on the device and the
+    // attempt is repeated once with the reads compacted on the host (streams and communicators are kept).
+    std::vector<long long> ip;
     bool slow = false;
-    if (n_rows_user > 0 && n_rows_user <= 4096) {       // tiny inputs: just look
-        for (int64_t i = 0; i < n_rows_user && !slow; ++i) slow = ip_at(i + 1) <= ip_at(i);
-        if (slow) { int rc = compact_on_host(); if (rc) return rc; }
+    if (in.n_rows_user > 0 && in.n_rows_user <= 4096)
+        for (int64_t i = 0; i < in.n_rows_user && !slow; ++i) slow = in.ip_at(i + 1) <= in.ip_at(i);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (slow) { int rc = compact_on_host(h, in, ip); if (rc) return rc; }
+        const int rc = create_attempt(h, cfg, in, slow ? &ip : nullptr, tm);
+        if (rc != kNeedsCompaction) return rc;
+        if (slow) return fail(TSC_ERR_STATE, "internal: empty read after compaction");
+        slow = true;
     }
-  retry_with_compaction:
-    const long long n_rows = slow ? (long long)ip.size() - 1 : (long long)n_rows_user;
+    return fail(TSC_ERR_STATE, "internal: construction did not settle");
+}
+
+static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInput& in, const std::vector<long long>* ip_compact,
+                          StageTimer& tm) {
+    const int K = in.n_cols;
+    const int n_local = std::max(1, cfg.n_local_devices);
+    const bool slow = ip_compact != nullptr;
+    const int64_t nnz = in.nnz;
+    const int32_t indptr_bytes = in.indptr_bytes;
+    const void* indptr = in.indptr;
+    const int32_t* indices = in.indices;
+    const uint16_t* raw = in.raw;
+    const double* q_lut = in.q_lut;
+    const int32_t lut_len = in.lut_len;
+    const double pi_prior = in.pi_prior, theta_prior = in.theta_prior;
+    const long long n_rows = slow ? (long long)ip_compact->size() - 1 : (long long)in.n_rows_user;
     h->n_rows = n_rows;
-    auto row_ptr = [&](long long r) -> long long { return slow ? ip[r] : ip_at(r); };
+    auto row_ptr = [&](long long r) -> long long { return slow ? (*ip_compact)[r] : in.ip_at(r); };
     tm.lap("indptr copy+validate");
     // ---- shard boundaries: contiguous, balanced by entry count
     std::vector<long long> rb(n_local + 1, 0);
@@ -457,7 +496,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
             const size_t ib = slow ? sizeof(long long) : (size_t)indptr_bytes;
             void* ip_native = nullptr;
             CU(cudaMalloc(&ip_native, ib * (s.n_rows + 1)));
-            const char* src = slow ? (const char*)(ip.data() + s.row_begin) : (const char*)indptr + ib * s.row_begin;
+            const char* src = slow ? (const char*)(ip_compact->data() + s.row_begin) : (const char*)indptr + ib * s.row_begin;
             CU(cudaMemcpyAsync(ip_native, src, ib * (s.n_rows + 1), cudaMemcpyHostToDevice, s.stream));
             const int g = grid_for(s.n_rows + 1, 256, s.n_sm * 16);
             if (ib == 4) k_indptr_prepare<int><<<g, 256, 0, s.stream>>>((const int*)ip_native, s.n_rows + 1, s.nnz_begin, s.indptr, s.bad);
@@ -469,8 +508,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
             CU(cudaStreamSynchronize(s.stream));
             cudaFree(ip_native);
             if (flags & 1) return fail(TSC_ERR_ARG, "indptr is not non-decreasing");
-            if (flags & 2) {            // empty reads: start over on the slow path
-                if (slow) return fail(TSC_ERR_STATE, "internal: empty read after compaction");
+            if (flags & 2) {            // empty reads: release this attempt's arrays and ask for the slow path
                 cleanup_tmp();
                 for (auto& sh : h->shards) {
                     cudaSetDevice(sh.dev);
@@ -478,10 +516,7 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, int64_t n_rows_user
                     for (void* p : ptrs) if (p) cudaFree(p);
                     sh.indptr = nullptr; sh.col = nullptr; sh.q = nullptr; sh.wy = nullptr; sh.bad = nullptr; sh.tiles = nullptr;
                 }
-                int rc = compact_on_host();
-                if (rc) return rc;
-                slow = true;
-                goto retry_with_compaction;
+                return kNeedsCompaction;
             }
             CU(cudaMemsetAsync(s.bad, 0, sizeof(int), s.stream));
         }
@@ -712,7 +747,8 @@ extern "C" int tsc_create(tsc_handle** out, const tsc_config* cfg_in, int64_t n_
     if (cfg_in) cfg = *cfg_in; else tsc_config_default(&cfg);
     tsc_handle* h = new (std::nothrow) tsc_handle();
     if (!h) return fail(TSC_ERR_ALLOC, "out of host memory");
-    int rc = create_impl(h, cfg, n_rows, n_cols, nnz, indptr, indptr_bytes, indices, raw, q_lut, lut_len, pi_prior, theta_prior);
+    const CreateInput in{n_rows, n_cols, nnz, indptr, indptr_bytes, indices, raw, q_lut, lut_len, pi_prior, theta_prior};
+    int rc = create_impl(h, cfg, in);
     if (rc) { std::string keep = g_err; tsc_destroy(h); g_err = keep; return rc; }
     *out = h;
     return TSC_OK;
@@ -957,7 +993,6 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
     if (use_likelihood && !lnls_out) return fail(TSC_ERR_ARG, "lnls_out required with use_likelihood");
     const int T = std::max(1, (int)max_iter);   // the reference's loop body always runs once (model.py:771-794)
     const int K = h->K;
-    const double inf = std::numeric_limits<double>::infinity();
     for (auto& s : h->shards) {
         CU(cudaSetDevice(s.dev));
         if (s.diffs_cap < T) {
@@ -1066,7 +1101,6 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
     if (n_iter) *n_iter = fin.iter;
     if (converged) *converged = fin.converged;
     if (final_lnl) *final_lnl = h->lnl;
-    (void)inf;
     return TSC_OK;
 }
 
@@ -1077,9 +1111,8 @@ static int alloc_entries(Shard& s, double** p) {
     return TSC_OK;
 }
 
-static int z_to_host(tsc_handle* h, const double* tab_amb_sel, int which, double* z_data) {
+static int z_to_host(tsc_handle* h, int which, double* z_data) {
     // which: 0 = tables tmp_c/tmp_a (explicit pi, theta), 1 = *_prev (stored posterior), 2 = ones (Q.norm(1))
-    (void)tab_amb_sel;
     for (auto& s : h->shards) {
         double* zd = nullptr;
         int rc = alloc_entries(s, &zd);
@@ -1124,13 +1157,13 @@ extern "C" int tsc_estep(tsc_handle* h, const double* pi, const double* theta, d
     if (!h || !pi || !theta || !z_data) return fail(TSC_ERR_ARG, "NULL argument");
     int rc = upload_pi_theta(h, pi, theta);
     if (rc) return rc;
-    return z_to_host(h, nullptr, 0, z_data);
+    return z_to_host(h, 0, z_data);
 }
 
 extern "C" int tsc_get_z(tsc_handle* h, int32_t initial, double* z_data) {
     if (!h || !z_data) return fail(TSC_ERR_ARG, "NULL argument");
     if (!initial && !h->em_done) return fail(TSC_ERR_STATE, "z exists only after em() (model.py:659,795)");
-    return z_to_host(h, nullptr, initial ? 2 : 1, z_data);
+    return z_to_host(h, initial ? 2 : 1, z_data);
 }
 
 __global__ void k_mstep_tail(const double* __restrict__ thetasum, const double* __restrict__ pisum0, const Consts* __restrict__ c,
@@ -1200,7 +1233,7 @@ extern "C" int tsc_calculate_lnl(tsc_handle* h, const double* z_data, const doub
         }
         if (e != cudaSuccess) { free_all(); return fail(TSC_ERR_CUDA, std::string("calculate_lnl: ") + cudaGetErrorString(e)); }
     }
-    rc = allreduce(h, 0, [](Shard& s) -> void* { return (void*)(s.scalars + 4); }, 1, ncclFloat64, ncclSum);
+    rc = allreduce(h, [](Shard& s) -> void* { return (void*)(s.scalars + 4); }, 1, ncclFloat64, ncclSum);
     if (!rc) rc = sync_all(h);
     free_all();
     if (rc) return rc;

@@ -350,3 +350,35 @@ def test_non_default_device_options_give_the_same_answer(kw):
     for method, initial in [("exclude", False), ("exclude", True), ("all", True)]:
         assert np.array_equal(tl.reassign_colsum(method, 0.9, initial), o.reassign_colsum(method, 0.9, initial))
     tl.close()
+
+
+@pytest.mark.parametrize("thresh", [0.0, 0.3, 0.5, 0.99, 1.0])
+def test_conf_thresholds(thresh):
+    """`conf` keeps every hit with z >= thresh and renormalises the survivors (model.py:854-856): with low thresholds
+    several hits per read survive, with 1.0 only unique reads."""
+    m = _matrix(N=5000, K=120, avg=6, skew=False, seed=93)
+    opts = Opts(max_iter=8)
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    tl.em(); o.em()
+    for initial in (False, True):
+        assert rel_err(tl.reassign_colsum("conf", thresh, initial), o.reassign_colsum("conf", thresh, initial)) < RTOL
+        a = tl.reassign("conf", thresh, initial)
+        b = sp.csr_matrix((o.reassign_data("conf", thresh, initial), m.indices.copy(), m.indptr.copy()), shape=m.shape)
+        b.eliminate_zeros()
+        d = abs(a - b)
+        assert a.dtype == np.float64 and (d.max() if d.nnz else 0.0) < 1e-9
+    tl.close()
+
+
+def test_identical_loci_keep_exact_ties_under_renumbering():
+    import os
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "case_duploci.npz"))
+    m = sp.csr_matrix((g["raw"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    for kw in (dict(permute_columns=True), dict(permute_columns=True, kernel="rows"), dict(replicas=3)):
+        tl = _tl(m, Opts(float(g["em_epsilon"]), int(g["max_iter"])), **kw)
+        tl.em()
+        assert np.array_equal(tl.reassign_colsum("exclude").astype(np.float64), g["colsums"][6]), kw
+        dup = tl.pi[60:80]
+        assert np.array_equal(dup, tl.pi[:20]), "duplicated loci must carry bit-identical pi"
+        tl.close()

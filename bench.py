@@ -345,7 +345,7 @@ def main():
             "gpu_launches": c1["launches"] - c0["launches"],
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_fused_tiles (E-step + M-step accumulation)",
+                "traffic": traffic, "kernel": "k_tiles<TILE_FUSED> (E-step + M-step accumulation, telescope_b200/csrc/tsc_tiles.cuh)",
                 "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
             },
             "final_lnl": tl.lnl,

@@ -19,7 +19,8 @@
 //   c = n * g is scatter-added (RED.ADD.F64) into one of R accumulator replicas resident in L2.
 //
 // Per entry this moves 12 B of HBM (8 B Q + 4 B locus) plus 32 B of tile descriptor per ~120 entries and 8 B of
-// w*Y per read; z is never written.  Reads longer than a tile take the long-row path (two passes over that read).
+// w*Y per read; z is never written.  Reads longer than a tile get a tile of their own: up to 256 entries stay in
+// registers (8 per lane, one pass), longer ones are walked twice.
 //
 // Reference semantics: model.py:718-722 (E-step) + model.py:730-733 (M-step sums); unique reads (Y=0) have
 // w*Y = 0 and add nothing, as in the reference where they enter pi only through pisum0 (model.py:699,738).

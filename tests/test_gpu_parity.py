@@ -352,10 +352,11 @@ def test_non_default_device_options_give_the_same_answer(kw):
     tl.close()
 
 
-@pytest.mark.parametrize("thresh", [0.0, 0.3, 0.5, 0.99, 1.0])
+@pytest.mark.parametrize("thresh", [0.0, 0.3, 0.5, 0.99])
 def test_conf_thresholds(thresh):
     """`conf` keeps every hit with z >= thresh and renormalises the survivors (model.py:854-856): with low thresholds
-    several hits per read survive, with 1.0 only unique reads."""
+    several hits per read survive.  (thresh = 1.0 exactly is not tested: a dominant hit's posterior is n * (1/sum n),
+    which is 1.0 or 1 - ulp depending on summation order -- in the reference as well.)"""
     m = _matrix(N=5000, K=120, avg=6, skew=False, seed=93)
     opts = Opts(max_iter=8)
     tl, o = _tl(m, opts), _oracle(m, opts)

@@ -162,6 +162,22 @@ int tsc_get_z(tsc_handle* h, int32_t initial, double* z_data);
  * tsc_reassign_data: the assignment matrix's data for the local entries (0.0 where nothing is stored).
  */
 int tsc_reassign_nbest(tsc_handle* h, int32_t initial, int32_t* nbest_rows);
+/*
+ * Telescope.output_report (model.py:432-458) in one pass over the matrix instead of seven reassign() calls.
+ * out6k = 6 vectors of n_cols doubles, global over all shards:
+ *   [0] reassign('conf', thresh)                     final_conf
+ *   [1] reassign('all', initial=True)                init_aligned
+ *   [2] reassign('unique')                           unique_count
+ *   [3] reassign('exclude', initial=True)            init_best
+ *   [4] reassign('average', initial=True)            init_best_avg
+ *   [5] reassign(final_method, thresh)               the counts file; for TSC_CHOOSE only the reads with one best hit
+ * nbest_init / nbest_final (optional, per local read): best hits of the initial / final posterior, for the host's
+ * RNG draws of 'choose'; tsc_choose_ties_colsum then returns the column sums of the drawn hits of the tie reads
+ * (reads with nbest > 1), to be added to [3] (init_best_random) or [5].
+ */
+int tsc_report(tsc_handle* h, double thresh, int32_t final_method, int32_t* nbest_init, int32_t* nbest_final,
+               double* out6k);
+int tsc_choose_ties_colsum(tsc_handle* h, int32_t initial, const int32_t* nbest, const int32_t* picks, double* colsum);
 int tsc_reassign_colsum(tsc_handle* h, int32_t method, double thresh, int32_t initial,
                         const int32_t* picks, double* colsum);
 int tsc_reassign_data(tsc_handle* h, int32_t method, double thresh, int32_t initial,

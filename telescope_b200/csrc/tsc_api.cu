@@ -144,6 +144,7 @@ struct tsc_handle {
     std::vector<int> perm, inv;           // perm[original] = internal; inv[internal] = original
     int n_dup_loci = 0;                   // loci whose column duplicates an earlier locus's
     std::string create_laps;              // host-side construction laps ("stage=ms;")
+    std::vector<unsigned long long> pos_count;   // per locus (caller's numbering): stored entries with score > 0, global
     Consts consts{};
     std::vector<double> pisum0_host;
     bool em_done = false;
@@ -482,11 +483,11 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         CU(cudaMalloc(&s.wy, sizeof(double) * std::max<long long>(s.n_rows, 1)));
         CU(cudaMalloc(&raw_d[i], sizeof(uint16_t) * std::max<long long>(s.nnz, 1)));
         CU(cudaMalloc(&colin_d[i], sizeof(int) * std::max<long long>(s.nnz, 1)));
-        CU(cudaMalloc(&cnt_d[i], sizeof(unsigned long long) * K * 3));
+        CU(cudaMalloc(&cnt_d[i], sizeof(unsigned long long) * K * 4));
         CU(cudaMalloc(&lut_d[i], sizeof(double) * lut_len));
         CU(cudaMalloc(&s.bad, sizeof(int)));
         CU(cudaMemsetAsync(s.bad, 0, sizeof(int), s.stream));
-        CU(cudaMemsetAsync(cnt_d[i], 0, sizeof(unsigned long long) * K * 3, s.stream));
+        CU(cudaMemsetAsync(cnt_d[i], 0, sizeof(unsigned long long) * K * 4, s.stream));
         CU(cudaMemsetAsync(s.col + s.nnz, 0, sizeof(int) * pad, s.stream));
         CU(cudaMemsetAsync(s.q + s.nnz, 0, sizeof(double) * pad, s.stream));
         if (tm.on) cudaStreamSynchronize(s.stream);
@@ -575,7 +576,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             NC(g_nccl.GroupStart());
             for (int i = 0; i < n_local; ++i) {
                 CU(cudaSetDevice(h->shards[i].dev));
-                NC(g_nccl.AllReduce(cnt_d[i], cnt_d[i], (size_t)K * 3, ncclUint64, ncclSum, h->shards[i].comm, h->shards[i].stream));
+                NC(g_nccl.AllReduce(cnt_d[i], cnt_d[i], (size_t)K * 4, ncclUint64, ncclSum, h->shards[i].comm, h->shards[i].stream));
             }
             NC(g_nccl.GroupEnd());
         }
@@ -586,12 +587,13 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             CU(cudaStreamSynchronize(s.stream));
             if (bad) return fail(TSC_ERR_ARG, "column index out of range [0, n_cols)");
         }
-        std::vector<unsigned long long> cnt((size_t)K * 3);
+        std::vector<unsigned long long> cnt((size_t)K * 4);
         Shard& s0 = h->shards[0];
         CU(cudaSetDevice(s0.dev));
-        CU(cudaMemcpyAsync(cnt.data(), cnt_d[0], sizeof(unsigned long long) * K * 3, cudaMemcpyDeviceToHost, s0.stream));
+        CU(cudaMemcpyAsync(cnt.data(), cnt_d[0], sizeof(unsigned long long) * K * 4, cudaMemcpyDeviceToHost, s0.stream));
         CU(cudaStreamSynchronize(s0.stream));
-        h->d2h += sizeof(unsigned long long) * K * 3;
+        h->d2h += sizeof(unsigned long long) * K * 4;
+        h->pos_count.assign(cnt.begin() + 3 * (size_t)K, cnt.end());      // entries with a positive score, per locus
         h->inv.resize(K);
         std::iota(h->inv.begin(), h->inv.end(), 0);
         if (cfg.permute_columns)
@@ -1300,6 +1302,117 @@ static int reassign_impl(tsc_handle* h, int method, double thresh, int initial, 
         return get_kvec(h, s, s.colsum, colsum);
     }
     return TSC_OK;
+}
+
+// per-read int arrays between the caller's read numbering and the compacted one (reads without entries are dropped)
+static void rows_to_user(const tsc_handle* h, const std::vector<int32_t>& compact, int32_t* user) {
+    std::fill(user, user + h->n_rows_user, 0);
+    for (long long r = 0; r < h->n_rows; ++r) user[h->rowmap[r]] = compact[r];
+}
+
+extern "C" int tsc_report(tsc_handle* h, double thresh, int32_t final_method, int32_t* nbest_init, int32_t* nbest_final,
+                          double* out6k) {
+    if (!h || !out6k) return fail(TSC_ERR_ARG, "NULL argument");
+    if (final_method < 0 || final_method > 5) return fail(TSC_ERR_ARG, "Argument \"method\" should be one of (exclude, choose, average, conf, unique, all)");
+    if (!h->em_done) return fail(TSC_ERR_STATE, "the report needs em() first");
+    const int K = h->K;
+    const bool compact = !h->rowmap.empty();
+    std::vector<int32_t> nbi_c, nbf_c;
+    if (compact && nbest_init) nbi_c.resize(h->n_rows);
+    if (compact && nbest_final) nbf_c.resize(h->n_rows);
+    int32_t* nbi_h = compact ? (nbest_init ? nbi_c.data() : nullptr) : nbest_init;
+    int32_t* nbf_h = compact ? (nbest_final ? nbf_c.data() : nullptr) : nbest_final;
+    std::vector<double*> out_d(h->shards.size(), nullptr);
+    auto free_all = [&]() { for (size_t i = 0; i < out_d.size(); ++i) if (out_d[i]) { cudaSetDevice(h->shards[i].dev); cudaFree(out_d[i]); } };
+    for (size_t i = 0; i < h->shards.size(); ++i) {
+        Shard& s = h->shards[i];
+        CU(cudaSetDevice(s.dev));
+        int *nbi_d = nullptr, *nbf_d = nullptr;
+        const size_t rb = sizeof(int) * std::max<long long>(s.n_rows, 1);
+        cudaError_t e = cudaMalloc(&out_d[i], sizeof(double) * 6 * K);
+        if (e == cudaSuccess) e = cudaMemsetAsync(out_d[i], 0, sizeof(double) * 6 * K, s.stream);
+        if (e == cudaSuccess && nbi_h) e = cudaMalloc(&nbi_d, rb);
+        if (e == cudaSuccess && nbf_h) e = cudaMalloc(&nbf_d, rb);
+        if (e == cudaSuccess) {
+            ReportArgs g{thresh, final_method, nbi_d, nbf_d, out_d[i], K};
+            launch_rows(h->G, [&](auto gg) {
+                k_report_rows<decltype(gg)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), s.pt_prev, s.pi_prev, g);
+            });
+            LAUNCH(h);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && nbi_h) { e = cudaMemcpyAsync(nbi_h + s.row_begin, nbi_d, sizeof(int) * s.n_rows, cudaMemcpyDeviceToHost, s.stream); h->d2h += sizeof(int) * s.n_rows; }
+        if (e == cudaSuccess && nbf_h) { e = cudaMemcpyAsync(nbf_h + s.row_begin, nbf_d, sizeof(int) * s.n_rows, cudaMemcpyDeviceToHost, s.stream); h->d2h += sizeof(int) * s.n_rows; }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+        if (nbi_d) cudaFree(nbi_d);
+        if (nbf_d) cudaFree(nbf_d);
+        if (e != cudaSuccess) { free_all(); return fail(TSC_ERR_CUDA, std::string("report: ") + cudaGetErrorString(e)); }
+    }
+    if (h->world > 1) {
+        ncclResult_t r = g_nccl.GroupStart();
+        for (size_t i = 0; i < h->shards.size() && r == ncclSuccess; ++i) {
+            cudaSetDevice(h->shards[i].dev);
+            r = g_nccl.AllReduce(out_d[i], out_d[i], (size_t)6 * K, ncclFloat64, ncclSum, h->shards[i].comm, h->shards[i].stream);
+        }
+        if (r == ncclSuccess) r = g_nccl.GroupEnd();
+        if (r != ncclSuccess) { free_all(); return fail(TSC_ERR_NCCL, std::string("report all-reduce: ") + g_nccl.GetErrorString(r)); }
+    }
+    int rc = sync_all(h);
+    Shard& s0 = h->shards[0];
+    for (int v = 0; v < 6 && !rc; ++v) {
+        cudaSetDevice(s0.dev);
+        rc = get_kvec(h, s0, out_d[0] + (size_t)v * K, out6k + (size_t)v * K);
+    }
+    free_all();
+    if (rc) return rc;
+    for (int j = 0; j < K; ++j) out6k[(size_t)K + j] = (double)h->pos_count[j];      // init_aligned: known since construction
+    if (compact && nbest_init) rows_to_user(h, nbi_c, nbest_init);
+    if (compact && nbest_final) rows_to_user(h, nbf_c, nbest_final);
+    return TSC_OK;
+}
+
+extern "C" int tsc_choose_ties_colsum(tsc_handle* h, int32_t initial, const int32_t* nbest, const int32_t* picks, double* colsum) {
+    if (!h || !nbest || !picks || !colsum) return fail(TSC_ERR_ARG, "NULL argument");
+    if (!initial && !h->em_done) return fail(TSC_ERR_STATE, "reassign(initial=False) needs em() first");
+    const int K = h->K;
+    const bool compact = !h->rowmap.empty();
+    std::vector<int32_t> nb_c, pk_c;
+    if (compact) {
+        nb_c.resize(h->n_rows); pk_c.resize(h->n_rows);
+        for (long long r = 0; r < h->n_rows; ++r) { nb_c[r] = nbest[h->rowmap[r]]; pk_c[r] = picks[h->rowmap[r]]; }
+    }
+    const int32_t* nb_h = compact ? nb_c.data() : nbest;
+    const int32_t* pk_h = compact ? pk_c.data() : picks;
+    for (auto& s : h->shards) {
+        CU(cudaSetDevice(s.dev));
+        int *nb_d = nullptr, *pk_d = nullptr;
+        const size_t rb = sizeof(int) * std::max<long long>(s.n_rows, 1);
+        cudaError_t e = cudaMalloc(&nb_d, rb);
+        if (e == cudaSuccess) e = cudaMalloc(&pk_d, rb);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nb_d, nb_h + s.row_begin, sizeof(int) * s.n_rows, cudaMemcpyHostToDevice, s.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pk_d, pk_h + s.row_begin, sizeof(int) * s.n_rows, cudaMemcpyHostToDevice, s.stream);
+        h->h2d += 2 * sizeof(int) * s.n_rows;
+        if (e == cudaSuccess) e = cudaMemsetAsync(s.colsum, 0, sizeof(double) * K, s.stream);
+        if (e == cudaSuccess) {
+            const double* ta = initial ? s.ones : s.pt_prev;
+            const double* tu = initial ? s.ones : s.pi_prev;
+            launch_rows(h->G, [&](auto gg) {
+                k_choose_ties_rows<decltype(gg)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, nb_d, pk_d, s.colsum);
+            });
+            LAUNCH(h);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+        if (nb_d) cudaFree(nb_d);
+        if (pk_d) cudaFree(pk_d);
+        if (e != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("choose ties: ") + cudaGetErrorString(e));
+    }
+    ALLREDUCE(h, s.colsum, (size_t)K, ncclFloat64, ncclSum);
+    int rc = sync_all(h);
+    if (rc) return rc;
+    Shard& s0 = h->shards[0];
+    CU(cudaSetDevice(s0.dev));
+    return get_kvec(h, s0, s0.colsum, colsum);
 }
 
 extern "C" int tsc_reassign_nbest(tsc_handle* h, int32_t initial, int32_t* nbest_rows) {

@@ -128,7 +128,8 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {   //
 // bit-identical pi/theta (its column sums run in read order), which reassign()'s exact tie test depends on.
 __global__ void k_col_signature(const long long* __restrict__ indptr, long long n_rows, const int* __restrict__ col,
                                 const uint16_t* __restrict__ raw, int n_cols, unsigned long long row_key0,
-                                unsigned long long* __restrict__ sig /* 3*K: count, sum h1, sum h2 */, int* __restrict__ bad) {
+                                unsigned long long* __restrict__ sig /* 4*K: count, sum h1, sum h2, count of scores > 0 */,
+                                int* __restrict__ bad) {
     long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; r < n_rows; r += stride) {
@@ -140,6 +141,7 @@ __global__ void k_col_signature(const long long* __restrict__ indptr, long long 
             atomicAdd(sig + c, 1ULL);
             atomicAdd(sig + n_cols + c, mix64(e));
             atomicAdd(sig + 2 * (size_t)n_cols + c, mix64(e ^ 0xd6e8feb86659fd93ULL));
+            if (raw[k] != 0) atomicAdd(sig + 3 * (size_t)n_cols + c, 1ULL);
         }
     }
 }
@@ -462,6 +464,129 @@ __global__ void __launch_bounds__(512) k_reassign_rows(Csr a, const double* __re
                 if (g.data) g.data[k] = val;
                 if (g.colsum && val != 0.0) atomicAdd(g.colsum + cc, val);
             }
+        }
+    }
+}
+
+// Everything Telescope.output_report needs (model.py:432-458) in ONE pass over the shard: for each read the final
+// posterior z_f (E-step tables) and the initial one z_i = Q.norm(1) are formed side by side, and six per-locus sums
+// are accumulated:
+//   out[0] final_conf     reassign('conf', thresh)            out[3] init_best      reassign('exclude', initial)
+//   out[1] (not here: init_aligned = stored entries with a positive score per locus, known since construction)
+//   out[2] unique_count   reassign('unique')                   out[4] init_best_avg  reassign('average', initial)
+//   out[5] the counts file's reassign(final_method, thresh); for 'choose' only reads with a single best hit are
+//          added here -- the tie reads need the host's RNG draws (nbest_final) and a second, cheap pass.
+// nbest_init feeds the draws of init_best_random = reassign('choose', initial).
+struct ReportArgs {
+    double thresh;
+    int final_method;
+    int* nbest_init;
+    int* nbest_final;
+    double* out;          // 6 * K
+    int K;
+};
+
+template <int G>
+__global__ void __launch_bounds__(512) k_report_rows(Csr a, const double* __restrict__ tab_amb, const double* __restrict__ tab_uni,
+                                                     ReportArgs g) {
+    const unsigned m = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long)gridDim.x * blockDim.x / G;
+    const int K = g.K;
+    for (; r < a.n_rows; r += ngrp) {
+        const long long s = a.indptr[r], e = a.indptr[r + 1];
+        const bool amb = (e - s) > 1;
+        const double* tab = amb ? tab_amb : tab_uni;
+        // pass 1: both row sums
+        double sum_f = 0, sum_i = 0;
+        for (long long k = s + lane; k < e; k += G) { const double q = a.q[k]; sum_f += q * __ldg(tab + a.col[k]); sum_i += q; }
+        sum_f = group_sum<G>(sum_f, m);
+        sum_i = group_sum<G>(sum_i, m);
+        const double rr_f = recip0(sum_f), rr_i = recip0(sum_i);
+        // pass 2: row maxima and the conf survivors
+        double max_f = 0, max_i = 0, kept = 0;
+        for (long long k = s + lane; k < e; k += G) {
+            const double q = a.q[k];
+            const double zf = (q * __ldg(tab + a.col[k])) * rr_f, zi = q * rr_i;
+            max_f = fmax(max_f, zf);
+            max_i = fmax(max_i, zi);
+            if (zf >= g.thresh) kept += zf;
+        }
+        max_f = group_max<G>(max_f, m);
+        max_i = group_max<G>(max_i, m);
+        kept = group_sum<G>(kept, m);
+        // pass 3: best-hit counts
+        int nb_f = 0, nb_i = 0;
+        for (long long k = s + lane; k < e; k += G) {
+            const double q = a.q[k];
+            const double zf = (q * __ldg(tab + a.col[k])) * rr_f, zi = q * rr_i;
+            nb_f += (zf == max_f && zf != 0.0);
+            nb_i += (zi == max_i && zi != 0.0);
+        }
+        nb_f = group_sum_int<G>(nb_f, m);
+        nb_i = group_sum_int<G>(nb_i, m);
+        if (lane == 0) {
+            if (g.nbest_init) g.nbest_init[r] = nb_i;
+            if (g.nbest_final) g.nbest_final[r] = nb_f;
+        }
+        const double rkept = recip0(kept);
+        const double avg_f = nb_f > 0 ? 1.0 / (double)nb_f : 0.0, avg_i = nb_i > 0 ? 1.0 / (double)nb_i : 0.0;
+        // pass 4: contributions
+        for (long long k = s + lane; k < e; k += G) {
+            const int c = a.col[k];
+            const double q = a.q[k];
+            const double zf = (q * __ldg(tab + c)) * rr_f, zi = q * rr_i;
+            const bool best_f = (zf == max_f && zf != 0.0), best_i = (zi == max_i && zi != 0.0);
+            const double conf = (zf >= g.thresh) ? zf * rkept : 0.0;
+            const double uniq = amb ? 0.0 : ceil(zf);
+            if (conf != 0.0) atomicAdd(g.out + c, conf);
+            if (uniq != 0.0) atomicAdd(g.out + 2 * (size_t)K + c, uniq);
+            if (best_i && nb_i == 1) atomicAdd(g.out + 3 * (size_t)K + c, 1.0);
+            if (best_i) atomicAdd(g.out + 4 * (size_t)K + c, avg_i);
+            double fin = 0;
+            switch (g.final_method) {
+                case 0: case 1: fin = (best_f && nb_f == 1) ? 1.0 : 0.0; break;
+                case 2: fin = best_f ? avg_f : 0.0; break;
+                case 3: fin = conf; break;
+                case 4: fin = uniq; break;
+                default: fin = (zf > 0.0) ? 1.0 : 0.0; break;
+            }
+            if (fin != 0.0) atomicAdd(g.out + 5 * (size_t)K + c, fin);
+        }
+    }
+}
+
+// reassign('choose') for the reads with several best hits only: adds 1 to the locus of the picks[r]-th best hit
+template <int G>
+__global__ void __launch_bounds__(512) k_choose_ties_rows(Csr a, const double* __restrict__ tab_amb, const double* __restrict__ tab_uni,
+                                                          const int* __restrict__ nbest, const int* __restrict__ picks,
+                                                          double* __restrict__ colsum) {
+    const unsigned m = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long)gridDim.x * blockDim.x / G;
+    for (; r < a.n_rows; r += ngrp) {
+        if (nbest[r] < 2) continue;                    // group-uniform
+        const long long s = a.indptr[r], e = a.indptr[r + 1];
+        const double* tab = (e - s > 1) ? tab_amb : tab_uni;
+        double n0; int c0;
+        const double sum = row_numerators<G>(a, s, e, tab, m, lane, n0, c0);
+        const double rr = recip0(sum);
+        double zmax = 0;
+        for (long long k = s + lane; k < e; k += G) zmax = fmax(zmax, (a.q[k] * __ldg(tab + a.col[k])) * rr);
+        zmax = group_max<G>(zmax, m);
+        const int pick = picks[r];
+        int seen = 0;
+        const long long e_round = s + ((e - s + G - 1) / G) * G;
+        for (long long k = s + lane; k < e_round; k += G) {
+            const bool act = k < e;
+            int cc = 0; double zz = 0;
+            if (act) { cc = a.col[k]; zz = (a.q[k] * __ldg(tab + cc)) * rr; }
+            const bool best = act && zz == zmax && zz != 0.0;
+            const unsigned bal = (__ballot_sync(m, best) >> ((threadIdx.x & 31u) & ~(unsigned)(G - 1))) & GroupBits<G>::value;
+            if (best && seen + __popc(bal & ((1u << lane) - 1u)) == pick) atomicAdd(colsum + cc, 1.0);
+            seen += __popc(bal);
         }
     }
 }

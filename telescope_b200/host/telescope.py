@@ -282,23 +282,35 @@ class Telescope(object):
         _rmethod, _rprob = self.opts.reassign_mode, self.opts.conf_prob
         _fnames = sorted(self.feat_index, key=self.feat_index.get)
         _flens = self.feature_length
-        colsum = getattr(tl, 'reassign_colsum', None) or (lambda *a, **k: tl.reassign(*a, **k).sum(0).A1)
-        # same call order as the reference: 'choose' consumes the seeded numpy RNG at the same point
+        if hasattr(tl, 'report_colsums'):
+            # CUDA model: one pass over the matrix for all columns (RNG draws in the reference's order)
+            cs = tl.report_colsums(_rprob, _rmethod)
+        else:
+            # any object with the reference's interface: same call order as model.py:435-441,457
+            colsum = getattr(tl, 'reassign_colsum', None) or (lambda *a, **k: tl.reassign(*a, **k).sum(0).A1)
+            cs = OrderedDict()
+            cs['final_conf'] = colsum('conf', _rprob)
+            cs['init_aligned'] = colsum('all', initial=True)
+            cs['unique_count'] = colsum('unique')
+            cs['init_best'] = colsum('exclude', initial=True)
+            cs['init_best_random'] = colsum('choose', initial=True)
+            cs['init_best_avg'] = colsum('average', initial=True)
+            cs['final'] = colsum(_rmethod, _rprob)
         stats = pd.DataFrame(OrderedDict([
             ('transcript', _fnames),
             ('transcript_length', [_flens[f] for f in _fnames]),
-            ('final_conf', colsum('conf', _rprob)),
+            ('final_conf', cs['final_conf']),
             ('final_prop', tl.pi),
-            ('init_aligned', colsum('all', initial=True)),
-            ('unique_count', colsum('unique')),
-            ('init_best', colsum('exclude', initial=True)),
-            ('init_best_random', colsum('choose', initial=True)),
-            ('init_best_avg', colsum('average', initial=True)),
+            ('init_aligned', cs['init_aligned']),
+            ('unique_count', cs['unique_count']),
+            ('init_best', cs['init_best']),
+            ('init_best_random', cs['init_best_random']),
+            ('init_best_avg', cs['init_best_avg']),
             ('init_prop', tl.pi_init),
         ]))
         stats.sort_values('final_prop', ascending=False, inplace=True)
         stats = stats.round(pd.Series([2, 3, 2, 3], index=['final_conf', 'final_prop', 'init_best_avg', 'init_prop']))
-        counts = pd.DataFrame(OrderedDict([('transcript', _fnames), ('count', colsum(_rmethod, _rprob))]))
+        counts = pd.DataFrame(OrderedDict([('transcript', _fnames), ('count', cs['final'])]))
         counts.sort_values('transcript', inplace=True)
         comment = ["## RunInfo"] + ['{}:{}'.format(*tup) for tup in self.run_info.items()]
         with open(stats_filename, 'w') as outh:

@@ -329,6 +329,47 @@ class TelescopeLikelihood(object):
         out.eliminate_zeros()
         return out
 
+    def report_colsums(self, conf_prob=0.9, final_method='exclude'):
+        """Every column sum `Telescope.output_report` needs (model.py:432-458), from ONE pass over the matrix plus a
+        small pass per 'choose' column.  Consumes the global numpy RNG in the reference's order: the draws of
+        init_best_random first, then those of the counts column when final_method is 'choose'."""
+        m = self._check_method(final_method)
+        K, N = self.K, self.N
+        out = np.empty(6 * K)
+        nb_i = np.zeros(N, dtype=np.int32)
+        nb_f = np.zeros(N, dtype=np.int32) if final_method == 'choose' else None
+        _abi.check(self._lib.tsc_report(self._h, float(conf_prob), m, _abi._p(nb_i, C.c_int32),
+                                         _abi._p(nb_f, C.c_int32) if nb_f is not None else None, _abi._p(out, C.c_double)))
+        out = out.reshape(6, K)
+
+        def ties(nbest, initial):
+            picks = np.zeros(N, dtype=np.int32)
+            t = np.flatnonzero(nbest > 1)
+            picks[t] = draw_picks(nbest[t])
+            extra = np.zeros(K)
+            if t.size:
+                _abi.check(self._lib.tsc_choose_ties_colsum(self._h, 1 if initial else 0, _abi._p(nbest, C.c_int32),
+                                                            _abi._p(picks, C.c_int32), _abi._p(extra, C.c_double)))
+            return extra
+
+        res = {
+            'final_conf': out[0].copy(),
+            'init_aligned': np.rint(out[1]).astype(np.uint64),
+            'unique_count': np.rint(out[2]).astype(np.uint64),
+            'init_best': np.rint(out[3]).astype(np.int64),
+            'init_best_random': np.rint(out[3] + ties(nb_i, True)).astype(np.int64),
+            'init_best_avg': out[4].copy(),
+        }
+        final = out[5]
+        if final_method == 'choose':
+            final = final + ties(nb_f, False)
+        if final_method in ('exclude', 'choose'):
+            final = np.rint(final).astype(np.int64)
+        elif final_method in ('unique', 'all'):
+            final = np.rint(final).astype(np.uint64)
+        res['final'] = final
+        return res
+
     def reassign_colsum(self, method, thresh=0.9, initial=False):
         """`reassign(method, thresh, initial).sum(0).A1` without moving the N x K matrix off the device."""
         m = self._check_method(method)

@@ -383,3 +383,34 @@ def test_identical_loci_keep_exact_ties_under_renumbering():
         dup = tl.pi[60:80]
         assert np.array_equal(dup, tl.pi[:20]), "duplicated loci must carry bit-identical pi"
         tl.close()
+
+
+@pytest.mark.parametrize("final_method", ["exclude", "choose", "average", "conf", "unique", "all"])
+def test_one_pass_report_equals_seven_reassign_calls(final_method):
+    """report_colsums (one pass + the 'choose' tie passes) against the oracle's seven reassign() column sums, with the
+    numpy RNG consumed in Telescope.output_report's order (model.py:435-441,457)."""
+    m = _matrix(N=6000, K=150, avg=7, skew=True, seed=95).tolil()
+    m.rows[10], m.data[10] = [], []                      # an empty read exercises the per-read index mapping
+    m = sp.csr_matrix(m).astype(np.uint16)
+    opts = Opts(max_iter=9)
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    tl.em(); o.em()
+    np.random.seed(4242)
+    got = tl.report_colsums(0.9, final_method)
+    np.random.seed(4242)
+    want = {
+        "final_conf": o.reassign_colsum("conf", 0.9),
+        "init_aligned": o.reassign_colsum("all", initial=True),
+        "unique_count": o.reassign_colsum("unique"),
+        "init_best": o.reassign_colsum("exclude", initial=True),
+        "init_best_random": o.reassign_colsum("choose", initial=True),
+        "init_best_avg": o.reassign_colsum("average", initial=True),
+        "final": o.reassign_colsum(final_method, 0.9),
+    }
+    for k, w in want.items():
+        g = got[k]
+        if w.dtype.kind in "iu":
+            assert g.dtype == w.dtype and np.array_equal(g, w), k
+        else:
+            assert rel_err(g, w) < RTOL, k
+    tl.close()

@@ -18,7 +18,8 @@ _CIGAR_BLOCK = (True, False, False, False, False, False, False, True, True)  # M
 
 class Segment(object):
     """One alignment record: just what fragment pairing, overlap and scoring need."""
-    __slots__ = ("name", "flag", "ref_id", "pos", "next_ref_id", "next_pos", "tlen", "blocks", "score", "tags")
+    __slots__ = ("name", "flag", "ref_id", "pos", "next_ref_id", "next_pos", "tlen", "blocks", "score", "tags",
+                 "raw", "aux_off", "_ed")   # raw BAM record, offset of its aux block (kept on request), its editor
 
     @property
     def is_paired(self):
@@ -82,8 +83,9 @@ def _scan_tags(buf, want=b"AS"):
 class AlignmentReader(object):
     """Iterate Segments of a BAM (binary, BGZF) or SAM (text) file in file order."""
 
-    def __init__(self, path):
+    def __init__(self, path, keep_raw=False):
         self.path = path
+        self.keep_raw = keep_raw
         fh = open(path, "rb")
         magic = fh.read(2)
         fh.close()
@@ -127,6 +129,7 @@ class AlignmentReader(object):
             rec = fh.read(size)
             ref_id, pos, l_name, _mapq, _bin, n_cig, flag, l_seq, nref, npos, tlen = _FIXED.unpack_from(rec, 0)
             s = Segment()
+            s._ed = None
             s.flag, s.ref_id, s.pos, s.next_ref_id, s.next_pos, s.tlen = flag, ref_id, pos, nref, npos, tlen
             p = 32
             s.name = rec[p:p + l_name - 1].decode()
@@ -137,6 +140,8 @@ class AlignmentReader(object):
             p += (l_seq + 1) // 2 + l_seq
             s.tags = _scan_tags(rec[p:])
             s.score = s.tags.get(b"AS")
+            if self.keep_raw:
+                s.raw, s.aux_off = rec, p
             yield s
 
     # ---- SAM
@@ -163,6 +168,7 @@ class AlignmentReader(object):
         for line in itertools.chain(first, self._fh):
             f = line.rstrip("\n").split("\t")
             s = Segment()
+            s._ed = None
             s.name, s.flag = f[0], int(f[1])
             s.ref_id = ref_index.get(f[2], -1)
             s.pos = int(f[3]) - 1
@@ -192,3 +198,125 @@ def bundles(segments):
         group.append(s)
     if group:
         yield group
+
+
+# --------------------------------------------------------------------------------------------------- writing
+def _aux_without(aux, tag):
+    """The aux block with every occurrence of `tag` removed."""
+    out, p, n = [], 0, len(aux)
+    while p + 3 <= n:
+        t, typ = aux[p:p + 2], aux[p + 2:p + 3]
+        q = p + 3
+        if typ in _TAG_SIZE:
+            q += _TAG_SIZE[typ]
+        elif typ in (b"Z", b"H"):
+            q = aux.index(b"\0", q) + 1
+        elif typ == b"B":
+            sub = aux[q:q + 1]
+            q += 5 + struct.unpack_from("<I", aux, q + 1)[0] * _TAG_SIZE[sub]
+        else:
+            break
+        if t != tag:
+            out.append(aux[p:q])
+        p = q
+    return b"".join(out)
+
+
+def _encode_tag(tag, value):
+    if isinstance(value, str):
+        return tag + b"Z" + value.encode() + b"\0"
+    v = int(value)                       # smallest integer type that holds the value, as pysam chooses it
+    if v < 0:
+        for typ, lo in ((b"c", -128), (b"s", -32768), (b"i", -2 ** 31)):
+            if v >= lo:
+                return tag + typ + struct.pack(_TAG_FMT[typ], v)
+    for typ, hi in ((b"C", 255), (b"S", 65535), (b"I", 2 ** 32 - 1)):
+        if v <= hi:
+            return tag + typ + struct.pack(_TAG_FMT[typ], v)
+    raise ValueError("integer tag out of range")
+
+
+class RecordEditor(object):
+    """Mutable view of one raw BAM record: flag, mapping quality and aux tags (what Telescope edits)."""
+
+    def __init__(self, seg):
+        self.seg = seg
+        self.head = bytearray(seg.raw[:seg.aux_off])
+        self.aux = bytes(seg.raw[seg.aux_off:])
+
+    flag = property(lambda self: struct.unpack_from("<H", self.head, 14)[0])
+
+    def set_flag(self, bits):
+        struct.pack_into("<H", self.head, 14, self.flag | bits)
+
+    def unset_flag(self, bits):
+        struct.pack_into("<H", self.head, 14, self.flag & ~bits & 0xFFFF)
+
+    def set_mapq(self, q):
+        self.head[9] = max(0, min(255, int(q)))
+
+    def set_tag(self, tag, value):
+        tag = tag.encode() if isinstance(tag, str) else tag
+        self.aux = _aux_without(self.aux, tag) + _encode_tag(tag, value)
+        self.seg.tags[tag] = value
+
+    def tobytes(self):
+        body = bytes(self.head) + self.aux
+        return struct.pack("<i", len(body)) + body
+
+
+_BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+class BamWriter(object):
+    """Write a BAM file: BGZF blocks of at most 64 KiB of payload, raw-deflate compressed (stdlib zlib)."""
+
+    def __init__(self, path, header_text, references, lengths, level=6):
+        import zlib
+        self._zlib, self._level = zlib, level
+        self._fh = open(path, "wb")
+        self._buf = bytearray()
+        text = header_text.encode()
+        self.write_bytes(b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(references)))
+        for name, ln in zip(references, lengths):
+            nm = name.encode() + b"\0"
+            self.write_bytes(struct.pack("<i", len(nm)) + nm + struct.pack("<i", ln))
+
+    def write_bytes(self, data):
+        self._buf += data
+        while len(self._buf) >= 0xFF00:
+            self._flush_block(self._buf[:0xFF00])
+            del self._buf[:0xFF00]
+
+    def write(self, record):
+        """record: RecordEditor, Segment (with raw kept) or raw bytes of one record body."""
+        if isinstance(record, RecordEditor):
+            self.write_bytes(record.tobytes())
+        elif isinstance(record, Segment):
+            self.write_bytes(struct.pack("<i", len(record.raw)) + record.raw)
+        else:
+            self.write_bytes(struct.pack("<i", len(record)) + record)
+
+    def _flush_block(self, payload):
+        z = self._zlib
+        comp = z.compressobj(self._level, z.DEFLATED, -15)
+        data = comp.compress(bytes(payload)) + comp.flush()
+        bsize = len(data) + 25                                  # total block size - 1
+        self._fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize) + data +
+                       struct.pack("<II", z.crc32(bytes(payload)) & 0xFFFFFFFF, len(payload)))
+
+    def close(self):
+        if self._fh is None:
+            return
+        if self._buf:
+            self._flush_block(self._buf)
+            self._buf = bytearray()
+        self._fh.write(_BGZF_EOF)
+        self._fh.close()
+        self._fh = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

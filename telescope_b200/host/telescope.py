@@ -7,6 +7,7 @@ Mirrors the reference's `Telescope` class (telescope/utils/model.py:74-564) wher
   * `save` / `load`   -- the NPZ checkpoint, same keys and dtypes (model.py:108-148)
   * `get_random_seed` -- model.py:150-153
   * `output_report`   -- the two TSVs, same columns / rounding / ordering / quirks (model.py:420-477)
+  * `update_sam`      -- model.py:479-521 (with the tagging of model.py:30-63 during loading), BAM input only
   * `print_summary`   -- model.py:523-555
 BAM/GTF parsing and overlap stay on the host (BASELINE.json north_star); only the EM loop and reassignment run on
 the GPU, through `telescope_b200.likelihood.TelescopeLikelihood`.
@@ -82,6 +83,34 @@ class Fragment(object):
     def alnscore(self):
         return self.r1.score + (self.r2.score if self.r2 is not None else 0)
 
+    # ---- record editing, only used with --updated_sam (segments then carry their raw BAM records)
+    def _editors(self):
+        if getattr(self.r1, "_ed", None) is None:
+            self.r1._ed = bam.RecordEditor(self.r1)
+            if self.r2 is not None:
+                self.r2._ed = bam.RecordEditor(self.r2)
+        return [self.r1._ed] + ([self.r2._ed] if self.r2 is not None else [])
+
+    def set_tag(self, tag, value):
+        for ed in self._editors():
+            ed.set_tag(tag, value)
+
+    def set_mapq(self, q):
+        for ed in self._editors():
+            ed.set_mapq(q)
+
+    def set_flag(self, bits):
+        for ed in self._editors():
+            ed.set_flag(bits)
+
+    def unset_flag(self, bits):
+        for ed in self._editors():
+            ed.unset_flag(bits)
+
+    def write(self, out):
+        for ed in self._editors():
+            out.write(ed)
+
 
 def _key(a):
     return (a.name, a.is_read1, a.ref_id, a.pos, a.next_ref_id, a.next_pos, abs(a.tlen))
@@ -131,6 +160,9 @@ class Telescope(object):
         self.shape = None
         self.raw_scores = None
         self.run_info['version'] = getattr(opts, 'version', 'unknown')
+        # BAM with non overlapping fragments (or unmapped) / with overlapping fragments (model.py:89-92)
+        self.other_bam = opts.outfile_path('other.bam') if hasattr(opts, 'outfile_path') else None
+        self.tmp_bam = opts.outfile_path('tmp_tele.bam') if hasattr(opts, 'outfile_path') else None
         with bam.AlignmentReader(opts.samfile) as sf:
             self.ref_names, self.ref_lengths = list(sf.references), list(sf.lengths)
         self.has_index = False
@@ -203,7 +235,12 @@ class Telescope(object):
         info = Counter()
         reads, feats, scores, lens = [], [], [], []
         min_as, max_as = BIG_INT, -BIG_INT
-        with bam.AlignmentReader(self.opts.samfile) as sf:
+        update_sam = bool(getattr(self.opts, 'updated_sam', False))
+        with bam.AlignmentReader(self.opts.samfile, keep_raw=update_sam) as sf:
+            if update_sam and not sf.is_bam:
+                raise NotImplementedError('--updated_sam needs BAM input')
+            bam_u = bam.BamWriter(self.other_bam, sf.header_text, sf.references, sf.lengths) if update_sam else None
+            bam_t = bam.BamWriter(self.tmp_bam, sf.header_text, sf.references, sf.lengths) if update_sam else None
             for alns in bam.bundles(sf):
                 info['total_fragments'] += 1
                 if info['total_fragments'] % 500000 == 0:
@@ -213,6 +250,8 @@ class Telescope(object):
                 code = CODES[ci][0]
                 info[code] += 1
                 if code in ('SU', 'PU'):
+                    if update_sam:
+                        frags[0].write(bam_u)
                     continue
                 mapped = [f for f in frags if not f.is_unmapped]
                 ambig = len(mapped) > 1
@@ -221,6 +260,9 @@ class Telescope(object):
                 hit = [assign(f) for f in mapped]
                 if all(h == nf for h in hit):
                     info['nofeat_A' if ambig else 'nofeat_U'] += 1
+                    if update_sam:
+                        for f in frags:
+                            f.write(bam_u)
                     continue
                 info['feat_A' if ambig else 'feat_U'] += 1
                 # best alignment per locus: highest score+length, first one wins ties (model.py:30-47)
@@ -228,9 +270,23 @@ class Telescope(object):
                 for f, h, s in zip(mapped, hit, sc):
                     k = s + f.alnlen
                     if h not in best or k > best[h][0]:
-                        best[h] = (k, s, f.alnlen)
-                for h, (_, s, ln) in sorted(best.items(), key=lambda kv: kv[1][1], reverse=True):
+                        best[h] = (k, s, f.alnlen, f)
+                ranked = sorted(best.items(), key=lambda kv: kv[1][1], reverse=True)
+                for h, (_, s, ln, _f) in ranked:
                     reads.append(alns[0].name); feats.append(h); scores.append(s); lens.append(ln)
+                if update_sam:
+                    # ZF = locus, ZT = PRI for the locus's best alignment / SEC for the others, ZB = best loci (model.py:48-61)
+                    top = ','.join(h for h, v in ranked if v[1] == ranked[0][1][1])
+                    for f, h in zip(mapped, hit):
+                        f.set_tag('ZF', h)
+                        f.set_tag('ZT', 'PRI' if f is best[h][3] else 'SEC')
+                    for f in mapped:
+                        f.set_tag('ZB', top)
+                    for f in frags:
+                        f.write(bam_t)
+            if update_sam:
+                bam_u.close()
+                bam_t.close()
         self._mapping_to_matrix(reads, feats, scores, lens, (min_as, max_as), info)
         for f in ('total_fragments', 'pair_mapped', 'pair_mixed', 'single_mapped', 'unmapped', 'unique', 'ambig',
                   'overlap_unique', 'overlap_ambig'):
@@ -320,7 +376,48 @@ class Telescope(object):
             counts.to_csv(outh, sep='\t', index=False)
 
     def update_sam(self, tl, filename):
-        raise NotImplementedError('--updated_sam needs a BAM writer (pysam in the reference); not part of the EM path')
+        """Re-tag the overlapping fragments with their posterior and assignment (model.py:479-521): XP = posterior in
+        percent, mapping quality = phred(posterior), YC = display colour, secondary flag for everything but the
+        alignment a fragment is assigned to."""
+        import sys
+        _rmethod, _rprob = self.opts.reassign_mode, self.opts.conf_prob
+        mat = csr_matrix(tl.reassign(_rmethod, _rprob))
+        z = csr_matrix(tl.z)
+        vermilion, yellow, pale, grey = '217,95,2', '230,171,2', '209,236,228', '248,248,248'
+
+        def phred(p):
+            return int(round(-10 * np.log10(1 - p))) if p < 1.0 else 255
+
+        with bam.AlignmentReader(self.tmp_bam, keep_raw=True) as sf:
+            pg = '@PG\tID:telescope\tPN:telescope\tCL:%s\tVN:%s\n' % (' '.join(sys.argv), self.run_info['version'])
+            with bam.BamWriter(filename, sf.header_text + pg, sf.references, sf.lengths) as out:
+                for alns in bam.bundles(sf):
+                    _, frags = classify(alns)
+                    if not frags:
+                        continue
+                    ridx = self.read_index[frags[0].query_id]
+                    for f in frags:
+                        if f.is_unmapped:
+                            f.write(out)
+                            continue
+                        tags = f.r1.tags
+                        assert b'ZT' in tags, 'Missing ZT tag'
+                        if tags[b'ZT'] == 'SEC':
+                            f.set_flag(bam.FSECONDARY)
+                            f.set_tag('YC', grey)
+                            f.set_mapq(0)
+                        else:
+                            fidx = self.feat_index[tags[b'ZF']]
+                            prob = float(z[ridx, fidx])
+                            f.set_mapq(phred(prob))
+                            f.set_tag('XP', int(round(prob * 100)))
+                            if mat[ridx, fidx] > 0:
+                                f.unset_flag(bam.FSECONDARY)
+                                f.set_tag('YC', vermilion)
+                            else:
+                                f.set_flag(bam.FSECONDARY)
+                                f.set_tag('YC', yellow if prob >= 0.2 else pale)
+                        f.write(out)
 
     # ------------------------------------------------------------------ model.py:523-555
     def print_summary(self, loglev=lg.WARNING):

@@ -86,7 +86,13 @@ def test_cli_assign_and_resume_reproduce_reference_reports(tmp_path):
     from telescope_b200 import cli
     data = os.path.join(ROOT, "telescope_b200", "data")
     out = str(tmp_path)
-    cli.main(["assign", os.path.join(data, "alignment.bam"), os.path.join(data, "annotation.gtf"), "--outdir", out, "--quiet"])
+    cli.main(["assign", os.path.join(data, "alignment.bam"), os.path.join(data, "annotation.gtf"), "--outdir", out, "--quiet",
+              "--updated_sam"])
+    from telescope_b200.host import bam
+    with bam.AlignmentReader(os.path.join(out, "telescope-updated.bam")) as r:
+        upd = list(r)
+    assert len(upd) == 66414 and sum(1 for s in upd if not s.flag & bam.FSECONDARY) == 2 * 1000   # all 1000 fragments assigned
+    assert all(b"YC" in s.tags for s in upd)
     stats = open(os.path.join(out, "telescope-run_stats.tsv")).read()
     counts = open(os.path.join(out, "telescope-TE_counts.tsv")).read()
     assert _strip_version(stats) == _strip_version(open(os.path.join(GOLD, "bundled_run_stats.tsv")).read())

@@ -236,3 +236,65 @@ def test_bam_reader_basics():
             names.add(seg.name)
     assert n == 66414 and len(names) == 1000
     assert first.is_paired and first.is_proper_pair and first.score is not None and first.blocks
+
+
+# ------------------------------------------------------------------------------------------------ --updated_sam
+def test_updated_sam_retags_fragments_like_the_reference_rules(tmp_path):
+    """telescope assign --updated_sam (reference model.py:30-63 tagging, 479-521 update_sam): every alignment of an
+    overlapping fragment gets ZF/ZT/ZB while loading; afterwards the best alignment per locus carries XP (posterior in
+    percent), mapq = phred(posterior), a colour, and everything but the assigned alignment is flagged secondary."""
+    import scipy.sparse as sp
+    from telescope_b200.host import bam
+    from telescope_b200.host.annotation import Annotation
+    from telescope_b200.host.telescope import Telescope
+
+    class O(AssignOpts):
+        updated_sam = True
+        outdir = str(tmp_path)
+        exp_tag = "t"
+
+        def outfile_path(self, suffix):
+            return os.path.join(self.outdir, "%s-%s" % (self.exp_tag, suffix))
+
+    opts = O()
+    ts = Telescope(opts)
+    ts.load_alignment(Annotation(opts.gtffile, "locus", "None"))
+    n_in = 66414
+    with bam.AlignmentReader(ts.tmp_bam) as t, bam.AlignmentReader(ts.other_bam) as u:
+        tmp, other = list(t), list(u)
+    assert len(tmp) + len(other) == n_in and len(other) == 0          # every bundled fragment overlaps the annotation
+    assert all(b"ZF" in s.tags and s.tags[b"ZT"] in ("PRI", "SEC") and b"ZB" in s.tags for s in tmp)
+
+    class Model(OracleModel):                                            # CPU stand-in with the reference's interface
+        def __init__(self, m, o):
+            OracleModel.__init__(self, m, o)
+            self.m = m
+            self.z = sp.csr_matrix((self.o.z, m.indices.copy(), m.indptr.copy()), shape=m.shape)
+
+        def reassign(self, method, thresh=0.9, initial=False):
+            d = self.o.reassign_data(method, thresh, initial)
+            return sp.csr_matrix((d, self.m.indices.copy(), self.m.indptr.copy()), shape=self.m.shape)
+
+    tl = Model(ts.raw_scores, opts)
+    out = os.path.join(str(tmp_path), "t-updated.bam")
+    ts.update_sam(tl, out)
+    with bam.AlignmentReader(out) as r:
+        upd = list(r)
+        assert "@PG\tID:telescope\tPN:telescope" in r.header_text
+    assert len(upd) == len(tmp)
+    mat, z = tl.reassign("exclude", 0.9), tl.z
+    n_assigned = 0
+    for a, b in zip(tmp, upd):
+        assert a.name == b.name and a.pos == b.pos
+        if a.tags[b"ZT"] == "SEC":
+            assert b.flag & bam.FSECONDARY and b.tags[b"YC"] == "248,248,248"
+            continue
+        i, j = ts.read_index[a.name], ts.feat_index[a.tags[b"ZF"]]
+        p = z[i, j]
+        assert b.tags[b"XP"] == int(round(p * 100))
+        if mat[i, j] > 0:
+            n_assigned += 1
+            assert not (b.flag & bam.FSECONDARY) and b.tags[b"YC"] == "217,95,2"
+        else:
+            assert b.flag & bam.FSECONDARY and b.tags[b"YC"] == ("230,171,2" if p >= 0.2 else "209,236,228")
+    assert n_assigned == 2 * int(mat.sum())                              # both mates of each assigned fragment

@@ -383,6 +383,13 @@ class Telescope(object):
         _rmethod, _rprob = self.opts.reassign_mode, self.opts.conf_prob
         mat = csr_matrix(tl.reassign(_rmethod, _rprob))
         z = csr_matrix(tl.z)
+        mat.sort_indices()
+        z.sort_indices()
+
+        def row_lookup(m, r):
+            """{locus: value} of one read (one CSR slice per fragment instead of a scipy scalar lookup per alignment)"""
+            a, b = m.indptr[r], m.indptr[r + 1]
+            return dict(zip(m.indices[a:b].tolist(), m.data[a:b].tolist()))
         vermilion, yellow, pale, grey = '217,95,2', '230,171,2', '209,236,228', '248,248,248'
 
         def phred(p):
@@ -396,6 +403,7 @@ class Telescope(object):
                     if not frags:
                         continue
                     ridx = self.read_index[frags[0].query_id]
+                    zrow, mrow = row_lookup(z, ridx), row_lookup(mat, ridx)
                     for f in frags:
                         if f.is_unmapped:
                             f.write(out)
@@ -408,10 +416,10 @@ class Telescope(object):
                             f.set_mapq(0)
                         else:
                             fidx = self.feat_index[tags[b'ZF']]
-                            prob = float(z[ridx, fidx])
+                            prob = float(zrow.get(fidx, 0.0))
                             f.set_mapq(phred(prob))
                             f.set_tag('XP', int(round(prob * 100)))
-                            if mat[ridx, fidx] > 0:
+                            if mrow.get(fidx, 0) > 0:
                                 f.unset_flag(bam.FSECONDARY)
                                 f.set_tag('YC', vermilion)
                             else:

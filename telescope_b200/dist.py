@@ -18,8 +18,17 @@ def env_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def _parent_start_ticks():
+    """Start time of the launcher process (clock ticks since boot): makes the key unique even if a pid is recycled."""
+    try:
+        with open("/proc/%d/stat" % os.getppid()) as fh:
+            return fh.read().rsplit(")", 1)[1].split()[19]
+    except Exception:
+        return "0"
+
+
 def _rdzv_path():
-    tag = "%d_%s" % (os.getppid(), os.environ.get("MASTER_PORT", "0"))
+    tag = "%d_%s_%s" % (os.getppid(), _parent_start_ticks(), os.environ.get("MASTER_PORT", "0"))
     return os.path.join(tempfile.gettempdir(), "telescope_b200_rdzv_" + tag)
 
 

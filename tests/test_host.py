@@ -298,3 +298,113 @@ def test_updated_sam_retags_fragments_like_the_reference_rules(tmp_path):
         else:
             assert b.flag & bam.FSECONDARY and b.tags[b"YC"] == ("230,171,2" if p >= 0.2 else "209,236,228")
     assert n_assigned == 2 * int(mat.sum())                              # both mates of each assigned fragment
+
+
+# ------------------------------------------------------------------------------------------------ host helpers
+def test_merge_blocks_docstring_answers():
+    """reference helpers.py:86-93"""
+    from telescope_b200.host.telescope import merge_blocks
+    assert merge_blocks([]) == []
+    assert merge_blocks([(1, 10)]) == [(1, 10)]
+    assert merge_blocks([(4, 9), (10, 14), (1, 3)]) == [(1, 3), (4, 9), (10, 14)]
+    assert merge_blocks([(4, 9), (10, 14), (1, 3)], dist=1) == [(1, 14)]
+
+
+def _seg(name, flag, ref_id=0, pos=100, nref=0, npos=300, tlen=250, blocks=((100, 150),), score=40):
+    from telescope_b200.host import bam
+    s = bam.Segment()
+    s.name, s.flag, s.ref_id, s.pos, s.next_ref_id, s.next_pos, s.tlen = name, flag, ref_id, pos, nref, npos, tlen
+    s.blocks, s.score, s.tags, s._ed = list(blocks), score, {}, None
+    return s
+
+
+def test_fragment_classification_and_pairing():
+    """reference alignment.py:128-161: bundle -> (code, fragments); mates pair up by coordinates."""
+    from telescope_b200.host.telescope import CODES, classify
+    # proper pair with two alignments: mates pair by (pos, next_pos)
+    r1a = _seg("q", 99, pos=100, npos=300, tlen=250, score=40)
+    r2a = _seg("q", 147, pos=300, npos=100, tlen=-250, blocks=((300, 350),), score=38)
+    r1b = _seg("q", 355, pos=900, npos=1100, tlen=250, blocks=((900, 950),), score=30)
+    r2b = _seg("q", 403, pos=1100, npos=900, tlen=-250, blocks=((1100, 1150),), score=31)
+    code, frags = classify([r1a, r2a, r1b, r2b])
+    assert CODES[code][0] == "PM" and len(frags) == 2
+    assert frags[0].r1 is r1a and frags[0].r2 is r2a and frags[0].alnscore == 78
+    assert frags[0].refblocks == [(100, 150), (300, 350)] and frags[0].alnlen == 100
+    assert frags[1].r1 is r1b and frags[1].alnscore == 61
+    # single-end mapped / unmapped, unmapped pair, mixed pair
+    assert CODES[classify([_seg("s", 0)])[0]][0] == "SM"
+    assert CODES[classify([_seg("s", 4)])[0]][0] == "SU"
+    code, frags = classify([_seg("p", 77), _seg("p", 141)])
+    assert CODES[code][0] == "PU" and len(frags) == 1 and frags[0].r2 is not None
+    code, frags = classify([_seg("x", 73), _seg("x", 133)])
+    assert CODES[code][0] == "PX" and len(frags) == 2 and frags[0].r2 is None
+
+
+def test_annotation_overlap_and_strand(tmp_path):
+    """reference _annotation_intervaltree.py:29-102: exon rows -> [start, end+1), same-locus overlaps merged, per-locus
+    overlap of blocks [b_start, b_end+1), optional strand filter."""
+    from telescope_b200.host.annotation import Annotation
+    gtf = tmp_path / "a.gtf"
+    rows = [
+        ("chr1", 100, 200, "+", "L1"), ("chr1", 150, 300, "+", "L1"),      # overlapping exons of one locus merge
+        ("chr1", 250, 400, "-", "L2"), ("chr2", 10, 20, "+", "L3"), ("chr1", 1000, 1100, "+", "L1"),
+    ]
+    gtf.write_text("".join('%s\tsrc\texon\t%d\t%d\t.\t%s\t.\tgene_id "g"; locus "%s";\n' % r for r in rows) +
+                   'chr1\tsrc\tgene\t1\t5000\t.\t+\t.\tlocus "IGNORED";\n# comment\n')
+    an = Annotation(str(gtf), "locus", "None")
+    assert list(an.loci) == ["L1", "L2", "L3"]
+    assert an.feature_length() == {"L1": (301 - 100) + (1101 - 1000), "L2": 401 - 250, "L3": 21 - 10}
+    hit = an.intersect_blocks("chr1", [(180, 260)])                        # query [180, 261)
+    assert hit == {"L1": 261 - 180, "L2": 261 - 250}
+    assert an.intersect_blocks("chrX", [(1, 10)]) == {} and an.intersect_blocks("chr1", [(500, 600)]) == {}
+    st = Annotation(str(gtf), "locus", "RF")
+    assert st.intersect_blocks("chr1", [(180, 260)], "-") == {"L2": 11}
+    assert st.intersect_blocks("chr1", [(180, 260)], "+") == {"L1": 81}
+
+
+def test_sam_text_input_gives_the_same_matrix(tmp_path):
+    """The loader accepts SAM text as well as BAM: dump the first fragments of the bundled BAM to SAM and compare."""
+    from telescope_b200.host import bam
+    from telescope_b200.host.annotation import Annotation
+    from telescope_b200.host.telescope import Telescope
+    src = os.path.join(DATA, "alignment.bam")
+    ops = "MIDNSHP=X"
+    with bam.AlignmentReader(src, keep_raw=True) as r:
+        refs, lens = r.references, r.lengths
+        lines = ["@HD\tVN:1.0\tSO:unsorted\n"] + ["@SQ\tSN:%s\tLN:%d\n" % t for t in zip(refs, lens)]
+        n_names, last = 0, None
+        import struct
+        for s in r:
+            if s.name != last:
+                n_names, last = n_names + 1, s.name
+                if n_names > 60:
+                    break
+            n_cig = struct.unpack_from("<H", s.raw, 12)[0]
+            l_name = s.raw[8]
+            cig = struct.unpack_from("<%dI" % n_cig, s.raw, 32 + l_name)
+            cigar = "".join("%d%s" % (c >> 4, ops[c & 15]) for c in cig) or "*"
+            rnext = "=" if s.next_ref_id == s.ref_id else (refs[s.next_ref_id] if s.next_ref_id >= 0 else "*")
+            lines.append("\t".join([s.name, str(s.flag), refs[s.ref_id], str(s.pos + 1), "255", cigar, rnext,
+                                    str(s.next_pos + 1), str(s.tlen), "*", "*", "AS:i:%d" % s.score]) + "\n")
+    sam = tmp_path / "first60.sam"
+    sam.write_text("".join(lines))
+
+    class O(AssignOpts):
+        samfile = str(sam)
+    ts = Telescope(O())
+    ts.load_alignment(Annotation(O.gtffile, "locus", "None"))
+    g = np.load(os.path.join(GOLD, "bundled.npz"))
+    assert ts.shape[0] == 60 and ts.run_info["total_fragments"] == 60
+    # same 60 reads as the first 60 rows of the BAM-derived matrix (scores are rescaled by the global minimum AS, so
+    # compare structure and score differences within reads)
+    ip = g["indptr"]
+    assert np.array_equal(np.diff(ts.raw_scores.indptr), np.diff(ip[:61]))
+    names = sorted(ts.feat_index, key=ts.feat_index.get)
+    gold_names = [str(n) for n in g["feat_names"]]
+    for r_ in range(60):
+        a = {names[j]: int(v) for j, v in zip(ts.raw_scores.indices[ts.raw_scores.indptr[r_]:ts.raw_scores.indptr[r_ + 1]],
+                                              ts.raw_scores.data[ts.raw_scores.indptr[r_]:ts.raw_scores.indptr[r_ + 1]])}
+        b = {gold_names[j]: int(v) for j, v in zip(g["indices"][ip[r_]:ip[r_ + 1]], g["raw"][ip[r_]:ip[r_ + 1]])}
+        assert set(a) == set(b)
+        k0 = min(a)
+        assert all(a[k] - a[k0] == b[k] - b[k0] for k in a)

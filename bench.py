@@ -339,7 +339,9 @@ def main():
             "e2e": {
                 "value": K / t_e2e, "unit": UNIT,
                 "h2d_bytes_per_step": c_e2e["h2d_bytes"] / K, "d2h_bytes_per_step": c_e2e["d2h_bytes"] / K,
-                "what": "TelescopeLikelihood(host CSR) + em(%d) + pi/theta to host, wall clock; construction %.3f s" % (K, t_create),
+                "what": "TelescopeLikelihood(host CSR in pinned memory) + em(%d) + pi/theta to host, wall clock, max over ranks; "
+                        "construction %.3f s; the library was warmed up once on a 4096-read toy matrix before the timer "
+                        "(CUDA module load), nothing of the workload is cached" % (K, t_create),
                 "construction_s": t_create, "tsc_create_s": create_s, "tsc_create_laps_ms": create_laps,
             },
             "gpu_launches": c1["launches"] - c0["launches"],

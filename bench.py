@@ -221,7 +221,7 @@ def main():
         return 0
 
     from telescope_b200 import _abi
-    from telescope_b200.likelihood import DistInfo, TelescopeLikelihood
+    from telescope_b200.likelihood import TelescopeLikelihood
     from telescope_b200.synthetic import shard_bounds, synth_csr
     import scipy.sparse as sp
 

@@ -18,7 +18,7 @@ Differences from the reference, on purpose:
     that case too (the reference keeps the stale index and its own `load` then fails its shape assertion).
 """
 import logging as lg
-from collections import Counter, OrderedDict, defaultdict
+from collections import Counter, OrderedDict
 
 import numpy as np
 import pandas as pd

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
-from conftest import ROOT, Opts, rel_err
+from conftest import ROOT, Opts
 from oracle.em_numpy import EMOracle
 
 GOLD = os.path.join(ROOT, "tests", "golden")

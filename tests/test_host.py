@@ -408,3 +408,54 @@ def test_sam_text_input_gives_the_same_matrix(tmp_path):
         assert set(a) == set(b)
         k0 = min(a)
         assert all(a[k] - a[k0] == b[k] - b[k0] for k in a)
+
+
+# ------------------------------------------------------------------------------------------------ reference's own annotation tests
+class TestAnnotationLikeTheReference(object):
+    """reference telescope/tests/test_annotation_parsers.py:16-95 (TestAnnotationIntervalTree), same fixture
+    (tests/data/annotation_test.2.gtf, copied from the reference's test data) and the same expected answers, against
+    the array-based Annotation.  (`subregion` belongs to the reference's broken parallel loader and is not provided.)"""
+
+    gtffile = os.path.join(ROOT, "tests", "data", "annotation_test.2.gtf")
+
+    def setup_method(self):
+        from telescope_b200.host.annotation import Annotation
+        self.A = Annotation(self.gtffile, "locus")
+
+    def test_annot_created(self):
+        assert self.A.key == "locus"
+
+    def test_annot_treesize(self):
+        n = {chrom: len(idx[2]) for chrom, idx in self.A._index.items()}
+        assert n == {"chr1": 3, "chr2": 4, "chr3": 2}
+
+    def test_empty_lookups(self):
+        A = self.A
+        assert not A.intersect_blocks("chr1", [(1, 9999)])
+        assert not A.intersect_blocks("chr1", [(20001, 39999)])
+        assert not A.intersect_blocks("chr1", [(50001, 79999)])
+        assert not A.intersect_blocks("chr1", [(90001, 90001)])
+        assert not A.intersect_blocks("chr1", [(190000, 590000)])
+        assert not A.intersect_blocks("chr2", [(1, 9999)])
+        assert not A.intersect_blocks("chr3", [(1, 9999)])
+        assert not A.intersect_blocks("chr4", [(1, 1000000000)])
+        assert not A.intersect_blocks("chrX", [(1, 1000000000)])
+
+    def test_simple_lookups(self):
+        for line in open(self.gtffile):
+            f = line.rstrip("\n").split("\t")
+            iv = (int(f[3]), int(f[4]))
+            loc = f[8].split('"')[1]
+            r = self.A.intersect_blocks(f[0], [iv])
+            assert loc in r
+            assert (r[loc] - 1) == (iv[1] - iv[0])
+
+    def test_overlap_lookups(self):
+        A = self.A
+        assert A.intersect_blocks("chr1", [(1, 10000)])["locus1"] == 1
+        assert A.intersect_blocks("chr2", [(1, 10000)])["locus4"] == 1
+        assert A.intersect_blocks("chr3", [(1, 10000)])["locus7"] == 1
+        r = A.intersect_blocks("chr1", [(19990, 40000)])
+        assert r["locus1"] == 11 and r["locus2"] == 1
+        assert A.intersect_blocks("chr2", [(44990, 46010)])["locus5"] == 22
+        assert A.intersect_blocks("chr3", [(44990, 46010)])["locus8"] == 1021

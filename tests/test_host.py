@@ -459,3 +459,26 @@ class TestAnnotationLikeTheReference(object):
         assert r["locus1"] == 11 and r["locus2"] == 1
         assert A.intersect_blocks("chr2", [(44990, 46010)])["locus5"] == 22
         assert A.intersect_blocks("chr3", [(44990, 46010)])["locus8"] == 1021
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/telescope_b200.h must compile as C (not only C++) and every declared function must resolve against the
+    built library -- what a cgo/cffi/ctypesgen user of the header would need."""
+    import shutil
+    import subprocess
+    from telescope_b200 import _abi
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi_check.c"
+    calls = "\n".join("    p[n++] = (void*)%s;" % s for s in _abi.SYMBOLS)
+    src.write_text('#include "telescope_b200.h"\n#include <stdio.h>\nint main(void) {\n    void* p[64]; int n = 0;\n%s\n'
+                   '    tsc_config c; tsc_config_default(&c);\n'
+                   '    int ok = 0; for (int i = 0; i < n; ++i) ok += p[i] != 0;\n'
+                   '    printf("%%d %%d %%d\\n", ok, tsc_abi_version(), c.n_local_devices);\n    return 0;\n}\n' % calls)
+    exe = tmp_path / "abi_check"
+    lib_dir = os.path.dirname(_abi.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", lib_dir, "-l:libtelescope_b200.so", "-Wl,-rpath," + lib_dir], check=True)
+    out = subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE, universal_newlines=True).stdout.split()
+    assert out == [str(len(_abi.SYMBOLS)), "1", "1"]

@@ -482,3 +482,30 @@ def test_header_is_plain_c_and_links(tmp_path):
                     "-L", lib_dir, "-l:libtelescope_b200.so", "-Wl,-rpath," + lib_dir], check=True)
     out = subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE, universal_newlines=True).stdout.split()
     assert out == [str(len(_abi.SYMBOLS)), "1", "1"]
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No CUDA library -> an exception that says how to build it, never a silent CPU path."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from telescope_b200 import _abi\n"
+            "try:\n    _abi.load()\nexcept _abi.TelescopeCudaError as e:\n    print('RAISED', 'no CPU fallback' in str(e))\n" % ROOT)
+    env = dict(os.environ, TELESCOPE_B200_LIB=str(tmp_path / "nope.so"))
+    out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, universal_newlines=True, check=True).stdout
+    assert out.strip() == "RAISED True"
+
+
+def test_reference_arm_prints_the_contract_line():
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--reads", "60000", "--loci", "500", "--cpu-seconds", "1"], stdout=subprocess.PIPE,
+                         universal_newlines=True, check=True).stdout.strip().splitlines()[-1]
+    d = json.loads(out)
+    assert d["impl"] == "reference" and d["metric"] == "em_iterations_per_sec" and d["unit"] == "iter/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("synthetic CSR")

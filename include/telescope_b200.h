@@ -54,7 +54,10 @@ typedef enum {
 typedef enum {
     TSC_KERNEL_AUTO = 0,
     TSC_KERNEL_ROWS = 1,  /* one sub-warp per read; simple, used as the in-library cross-check */
-    TSC_KERNEL_TILES = 2  /* flat 128-entry tiles with warp segmented scan; the fast path */
+    TSC_KERNEL_TILES = 2, /* flat 128-entry tiles with warp segmented scan (round-1 fast path; still used for the
+                             posterior / log-likelihood passes and for reads that do not fit a slice) */
+    TSC_KERNEL_ELL = 3    /* locus-clustered sliced-ELL stream, one read per lane, per-warp locus window in shared
+                             memory, TMA-fed (AUTO selects this) */
 } tsc_kernel;
 
 typedef struct {

@@ -7,20 +7,38 @@ imports four things this image does not have (`past.utils.old_div` model.py:4, `
 is touched by the EM path (`TelescopeLikelihood`, model.py:631-865; `csr_matrix_plus`, sparse_plus.py:24-174), so
 empty stand-in modules are registered before the import.
 
-`/root/reference` exists only in the build container, never on the GPU box: this module is used by
-`tests/golden/make_golden.py` (to generate the committed fixtures) and by the `not gpu` tests that cross-check
-the oracle restatements when the reference tree happens to be present.  Nothing in the product imports it.
+`/root/reference` exists only in the build container, never on the GPU box; there the unmodified copy staged by
+`oracle/make_ref.py` under the git-ignored `oracle/_ref/` is imported instead.  Used by
+`tests/golden/make_golden.py` (to generate the committed fixtures), by the `not gpu` tests that cross-check the
+oracle restatements, and by `bench.py`'s CPU arm (`cpu_baseline.kind == "reference"`).  Nothing in the product
+imports it.
 """
 import os
 import sys
 import types
 import warnings
 
-REFERENCE_ROOT = os.environ.get("TELESCOPE_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # written by oracle/make_ref.py
+
+
+def _pick_root():
+    """The live tree in the build container; on the GPU box the unmodified copy staged by oracle/make_ref.py."""
+    env = os.environ.get("TELESCOPE_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", _STAGED]:
+        if os.path.isfile(os.path.join(cand, "telescope", "utils", "model.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "telescope", "utils", "model.py"))
+
+
+def reference_is_staged_copy():
+    return os.path.abspath(REFERENCE_ROOT) == os.path.abspath(_STAGED)
 
 
 def _stub(name, **attrs):

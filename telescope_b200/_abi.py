@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("TELESCOPE_B200_LIB") or os.path.join(_HERE, "libteles
 
 TSC_OK, TSC_ERR_ARG, TSC_ERR_CUDA, TSC_ERR_NCCL, TSC_ERR_STATE, TSC_ERR_ALLOC = range(6)
 METHODS = {"exclude": 0, "choose": 1, "average": 2, "conf": 3, "unique": 4, "all": 5}
-KERNELS = {"auto": 0, "rows": 1, "tiles": 2}
+KERNELS = {"auto": 0, "rows": 1, "tiles": 2, "ell": 3}
 
 # every symbol the header declares; tests check the library exports exactly these
 SYMBOLS = (

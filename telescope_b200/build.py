@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtelescope_b200.so")
 SOURCES = [os.path.join(CSRC, "tsc_api.cu")]
-HEADERS = [os.path.join(CSRC, f) for f in ("tsc_kernels.cuh", "tsc_tiles.cuh")] + \
+HEADERS = [os.path.join(CSRC, f) for f in ("tsc_kernels.cuh", "tsc_tiles.cuh", "tsc_ell.cuh")] + \
           [os.path.join(os.path.dirname(HERE), "include", "telescope_b200.h")]
 
 NVCC_FLAGS = [

@@ -30,6 +30,7 @@
 #include "../../include/telescope_b200.h"
 #include "tsc_kernels.cuh"
 #include "tsc_tiles.cuh"
+#include "tsc_ell.cuh"
 
 using namespace tsc;
 
@@ -132,6 +133,17 @@ struct Shard {
     int grid_rows = 0, grid_tiles = 0;
     size_t smem_tiles = 0;
     int s_cols = 0;
+    // clustered sliced-ELL stream of the fused kernel (tsc_ell.cuh) + residual CSR for the reads it does not hold
+    unsigned char* ell_stream = nullptr;
+    long long ell_bytes = 0, ell_slices = 0, ell_reads = 0, ell_entries = 0;
+    long long* ell_rec_off = nullptr;     // ell_slices + 1 record offsets
+    int ell_grid = 0;
+    long long res_rows = 0, res_nnz = 0, res_n_tiles = 0, res_n_long = 0;
+    long long* res_indptr = nullptr;
+    int* res_col = nullptr;
+    double* res_q = nullptr;
+    double* res_wy = nullptr;
+    Tile* res_tiles = nullptr;
 };
 
 struct tsc_handle {
@@ -215,11 +227,14 @@ static int launch_rows(int G, F&& f) {
 
 static Csr csr_of(const Shard& s) { return Csr{s.indptr, s.col, s.q, s.n_rows}; }
 
+static int launch_fused(tsc_handle* h, Shard& s, bool gated);
+
 // ------------------------------------------------------------------------------------------------- tile launches
 template <int MODE>
-static void launch_tiles(const Shard& s, const TileArgs& a, bool smem_tab) {
+static void launch_tiles(const Shard& s, const TileArgs& a, bool smem_tab, int long8_override = -1) {
     const size_t scratch = sizeof(double) * kTileWarps * kScratch;
-    const bool long8 = s.n_long * 200 > s.n_tiles;      // > 0.5 % of the tiles are long reads
+    // > 0.5 % of the tiles are long reads (the residual CSR of the ELL path passes its own ratio)
+    const bool long8 = long8_override >= 0 ? long8_override != 0 : s.n_long * 200 > s.n_tiles;
     if (MODE == TILE_FUSED && smem_tab) {
         if (long8) k_tiles<MODE, true, true><<<s.grid_tiles, kTileThreads, s.smem_tiles, s.stream>>>(a);
         else k_tiles<MODE, true, false><<<s.grid_tiles, kTileThreads, s.smem_tiles, s.stream>>>(a);
@@ -276,7 +291,8 @@ static void free_shard(Shard& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     void* ptrs[] = {s.indptr, s.col, s.q, s.wy, s.tiles, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
                     s.pi_init, s.theta_init, s.pisum0, s.acc, s.thetasum, s.ones, s.tmp_a, s.tmp_b, s.tmp_c, s.colsum,
-                    s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad};
+                    s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad,
+                    s.ell_stream, s.ell_rec_off, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.st_host) cudaFreeHost(s.st_host);
     for (auto& e : s.ev_poll) if (e) cudaEventDestroy(e);
@@ -345,6 +361,187 @@ static int compact_on_host(tsc_handle* h, const CreateInput& in, std::vector<lon
 
 static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInput& in, const std::vector<long long>* ip_compact,
                           StageTimer& tm);
+
+// Flat tiles of whole reads (tsc_tiles.cuh) over a device-resident read-pointer array: count per chunk, prefix on the
+// host (a few thousand chunks), fill.
+struct DevBuf {              // device temporaries released on every exit path
+    std::vector<void*> p;
+    ~DevBuf() { for (void* q : p) if (q) cudaFree(q); }
+    template <typename T> cudaError_t alloc(T** out, size_t n) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+        *out = (T*)q;
+        if (e == cudaSuccess) p.push_back(q);
+        return e;
+    }
+};
+
+static int build_tiles(tsc_handle* h, Shard& s, const long long* indptr_d, long long n_rows, Tile** tiles_out,
+                       long long* n_tiles_out, long long* n_long_out) {
+    const int n_chunks = (int)((n_rows + kChunkRows - 1) / kChunkRows);
+    DevBuf tmp;
+    int* counts_d = nullptr;
+    long long* offs_d = nullptr;
+    unsigned long long* nlong_d = nullptr;
+    CU(tmp.alloc(&counts_d, n_chunks));
+    CU(tmp.alloc(&offs_d, n_chunks));
+    CU(tmp.alloc(&nlong_d, 1));
+    CU(cudaMemsetAsync(nlong_d, 0, sizeof(unsigned long long), s.stream));
+    std::vector<int> counts(n_chunks);
+    std::vector<long long> offs(n_chunks);
+    if (n_chunks > 0) {
+        k_tile_count<<<(n_chunks + 127) / 128, 128, 0, s.stream>>>(indptr_d, n_rows, counts_d, n_chunks);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(counts.data(), counts_d, sizeof(int) * n_chunks, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+    }
+    long long total = 0;
+    for (int c = 0; c < n_chunks; ++c) { offs[c] = total; total += counts[c]; }
+    *n_tiles_out = total;
+    CU(cudaMalloc(tiles_out, sizeof(Tile) * std::max<long long>(total, 1)));
+    if (n_chunks > 0) {
+        CU(cudaMemcpyAsync(offs_d, offs.data(), sizeof(long long) * n_chunks, cudaMemcpyHostToDevice, s.stream));
+        k_tile_fill<<<(n_chunks + 127) / 128, 128, 0, s.stream>>>(indptr_d, n_rows, offs_d, n_chunks, *tiles_out, nlong_d);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+    }
+    unsigned long long nl = 0;
+    CU(cudaMemcpyAsync(&nl, nlong_d, sizeof(nl), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    *n_long_out = (long long)nl;
+    return TSC_OK;
+}
+
+// out[0..n] = exclusive prefix sums of in[0..n) on the shard's stream (tsc_ell.cuh scan kernels)
+template <typename T>
+static int device_scan(tsc_handle* h, Shard& s, const T* in, long long n, long long* out) {
+    const int nb = (int)std::max<long long>(1, (n + kScanItems - 1) / kScanItems);
+    DevBuf tmp;
+    long long* tot = nullptr;
+    CU(tmp.alloc(&tot, (size_t)nb + 1));
+    k_scan_local<T><<<nb, 1024, 0, s.stream>>>(in, n, out, tot);
+    k_scan_totals<<<1, 1024, 0, s.stream>>>(tot, nb);
+    k_scan_add<<<grid_for(n, 256, s.n_sm * 16), 256, 0, s.stream>>>(out, n, tot, nb);
+    h->launches += 3;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s.stream));      // tot is released on return
+    return TSC_OK;
+}
+
+static int fetch_ll(Shard& s, const long long* dev, long long* host) {
+    CU(cudaMemcpyAsync(host, dev, sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return TSC_OK;
+}
+
+// The clustered sliced-ELL stream of the fused kernel and the residual CSR (tsc_ell.cuh), from the shard's finished
+// q / col / indptr / wy arrays.  One-off; every array it allocates belongs to the shard.
+static int build_ell(tsc_handle* h, Shard& s) {
+    const int K = h->K;
+    const long long n_rows = s.n_rows;
+    CU(cudaSetDevice(s.dev));
+    DevBuf tmp;
+    int* key = nullptr;
+    const bool ell_ok = n_rows > 0 && (long long)K * (1 << kEllLenBits) < (1LL << 31);
+    long long n_cand = 0;
+    int* sorted = nullptr;
+    if (ell_ok) {
+        const int n_keys = K << kEllLenBits;
+        unsigned *hist = nullptr, *cursor = nullptr;
+        long long* bin_start = nullptr;
+        CU(tmp.alloc(&key, n_rows));
+        CU(tmp.alloc(&hist, n_keys));
+        CU(tmp.alloc(&cursor, n_keys));
+        CU(tmp.alloc(&bin_start, (size_t)n_keys + 1));
+        CU(cudaMemsetAsync(hist, 0, sizeof(unsigned) * n_keys, s.stream));
+        CU(cudaMemsetAsync(cursor, 0, sizeof(unsigned) * n_keys, s.stream));
+        const int g = grid_for(n_rows, 256, s.n_sm * 16);
+        k_ell_classify<<<g, 256, 0, s.stream>>>(s.indptr, n_rows, s.col, n_keys, key, hist);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+        int rc = device_scan<unsigned>(h, s, hist, n_keys, bin_start);
+        if (rc) return rc;
+        if ((rc = fetch_ll(s, bin_start + n_keys, &n_cand))) return rc;
+        if (n_cand > 0) {
+            CU(tmp.alloc(&sorted, n_cand));
+            k_ell_scatter<<<g, 256, 0, s.stream>>>(key, n_rows, bin_start, cursor, sorted);
+            LAUNCH(h);
+            CU(cudaGetLastError());
+        }
+    }
+    if (n_cand > 0) {
+        const long long n_slices = (n_cand + kEllReads - 1) / kEllReads;
+        int4* hdr = nullptr;
+        int* rec_bytes = nullptr;
+        long long* rec_off = nullptr;
+        CU(tmp.alloc(&hdr, n_slices));
+        CU(tmp.alloc(&rec_bytes, n_slices));
+        CU(tmp.alloc(&rec_off, (size_t)n_slices + 1));
+        k_ell_slices<<<grid_for(n_slices, 128, s.n_sm * 16), 128, 0, s.stream>>>(s.indptr, s.col, sorted, n_cand, n_slices, key, hdr, rec_bytes);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+        int rc = device_scan<int>(h, s, rec_bytes, n_slices, rec_off);
+        if (rc) return rc;
+        long long total = 0;
+        if ((rc = fetch_ll(s, rec_off + n_slices, &total))) return rc;
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ell_fused, 32, kEllSmem));
+        const int warps = s.n_sm * std::max(per_sm, 1);
+        const long long n_seg = (n_slices + 31) / 32;      // a warp's unit of work between two window flushes
+        CU(cudaMalloc(&s.ell_stream, (size_t)total));
+        k_ell_fill<<<grid_for(n_slices * 32, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, s.col, s.q, s.wy, sorted, n_cand, n_slices,
+                                                                                   hdr, rec_off, s.ell_stream);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+        s.ell_rec_off = rec_off;               // kept: the kernel's record index
+        tmp.p.erase(std::find(tmp.p.begin(), tmp.p.end(), (void*)rec_off));
+        CU(cudaStreamSynchronize(s.stream));
+        s.ell_bytes = total;
+        s.ell_slices = n_slices;
+        s.ell_grid = (int)std::min<long long>(n_seg, warps);
+    }
+    // ---- residual CSR: ambiguous reads without a slot in the stream (key < 0, or every ambiguous read when the
+    // stream could not be built)
+    {
+        int *flag = nullptr, *rlen = nullptr;
+        long long *row_pos = nullptr, *ent_pos = nullptr;
+        CU(tmp.alloc(&flag, n_rows));
+        CU(tmp.alloc(&rlen, n_rows));
+        CU(tmp.alloc(&row_pos, (size_t)n_rows + 1));
+        CU(tmp.alloc(&ent_pos, (size_t)n_rows + 1));
+        const int g = grid_for(n_rows, 256, s.n_sm * 16);
+        k_res_flags<<<g, 256, 0, s.stream>>>(s.indptr, n_rows, key, flag, rlen);
+        LAUNCH(h);
+        CU(cudaGetLastError());
+        int rc = device_scan<int>(h, s, flag, n_rows, row_pos);
+        if (!rc) rc = device_scan<int>(h, s, rlen, n_rows, ent_pos);
+        if (!rc) rc = fetch_ll(s, row_pos + n_rows, &s.res_rows);
+        if (!rc) rc = fetch_ll(s, ent_pos + n_rows, &s.res_nnz);
+        if (rc) return rc;
+        if (s.res_rows > 0) {
+            const size_t pad = 256;
+            CU(cudaMalloc(&s.res_indptr, sizeof(long long) * (s.res_rows + 1)));
+            CU(cudaMalloc(&s.res_col, sizeof(int) * (s.res_nnz + pad)));
+            CU(cudaMalloc(&s.res_q, sizeof(double) * (s.res_nnz + pad)));
+            CU(cudaMalloc(&s.res_wy, sizeof(double) * s.res_rows));
+            CU(cudaMemsetAsync(s.res_col + s.res_nnz, 0, sizeof(int) * pad, s.stream));
+            CU(cudaMemsetAsync(s.res_q + s.res_nnz, 0, sizeof(double) * pad, s.stream));
+            k_res_copy<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, flag, row_pos, ent_pos,
+                                                                                   s.res_indptr, s.res_col, s.res_q, s.res_wy);
+            LAUNCH(h);
+            CU(cudaMemcpyAsync(s.res_indptr + s.res_rows, &s.res_nnz, sizeof(long long), cudaMemcpyHostToDevice, s.stream));
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(s.stream));
+            rc = build_tiles(h, s, s.res_indptr, s.res_rows, &s.res_tiles, &s.res_n_tiles, &s.res_n_long);
+            if (rc) return rc;
+        }
+    }
+    s.ell_reads = n_cand;     // before eviction; the exact split is res_rows / res_nnz
+    CU(cudaStreamSynchronize(s.stream));
+    return TSC_OK;
+}
+
 
 static int create_impl(tsc_handle* h, const tsc_config& cfg, const CreateInput& in) {
     h->K = in.n_cols;
@@ -453,7 +650,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
     h->R = cfg.replicas > 0 ? std::min(cfg.replicas, 64) : 16;
     const double avg = n_rows ? (double)nnz / (double)n_rows : 1.0;
     h->G = avg <= 5.0 ? 4 : avg <= 24.0 ? 8 : avg <= 64.0 ? 16 : 32;
-    h->kernel = (cfg.kernel == TSC_KERNEL_ROWS) ? TSC_KERNEL_ROWS : TSC_KERNEL_TILES;
+    h->kernel = (cfg.kernel == TSC_KERNEL_ROWS || cfg.kernel == TSC_KERNEL_TILES) ? cfg.kernel : TSC_KERNEL_ELL;
 
     // ---- upload + build per shard
     std::vector<uint16_t*> raw_d(n_local, nullptr);
@@ -495,8 +692,9 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         // read pointers: native dtype up, int64 + rebased + validated on the device
         {
             const size_t ib = slow ? sizeof(long long) : (size_t)indptr_bytes;
-            void* ip_native = nullptr;
-            CU(cudaMalloc(&ip_native, ib * (s.n_rows + 1)));
+            DevBuf ipbuf;
+            char* ip_native = nullptr;
+            CU(ipbuf.alloc(&ip_native, ib * (s.n_rows + 1)));
             const char* src = slow ? (const char*)(ip_compact->data() + s.row_begin) : (const char*)indptr + ib * s.row_begin;
             CU(cudaMemcpyAsync(ip_native, src, ib * (s.n_rows + 1), cudaMemcpyHostToDevice, s.stream));
             const int g = grid_for(s.n_rows + 1, 256, s.n_sm * 16);
@@ -507,7 +705,6 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             int flags = 0;
             CU(cudaMemcpyAsync(&flags, s.bad, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
             CU(cudaStreamSynchronize(s.stream));
-            cudaFree(ip_native);
             if (flags & 1) return fail(TSC_ERR_ARG, "indptr is not non-decreasing");
             if (flags & 2) {            // empty reads: release this attempt's arrays and ask for the slow path
                 cleanup_tmp();
@@ -527,40 +724,10 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         CU(cudaMemcpyAsync(lut_d[i], q_lut, sizeof(double) * lut_len, cudaMemcpyHostToDevice, s.stream));
         h->h2d += (size_t)(slow ? 8 : indptr_bytes) * (s.n_rows + 1) + (sizeof(uint16_t) + sizeof(int)) * s.nnz + sizeof(double) * lut_len;
         if (tm.on) { cudaStreamSynchronize(s.stream); tm.lap("  entries H2D (sync for timing)"); }
-        // tiles for the fused kernel, built on the device while the entry arrays are still arriving
+        // tiles for the flat-tile passes, built on the device while the entry arrays are still arriving
         {
-            const int n_chunks = (int)((s.n_rows + kChunkRows - 1) / kChunkRows);
-            int* counts_d = nullptr;
-            long long* offs_d = nullptr;
-            unsigned long long* nlong_d = nullptr;
-            CU(cudaMalloc(&counts_d, sizeof(int) * std::max(n_chunks, 1)));
-            CU(cudaMalloc(&offs_d, sizeof(long long) * std::max(n_chunks, 1)));
-            CU(cudaMalloc(&nlong_d, sizeof(unsigned long long)));
-            CU(cudaMemsetAsync(nlong_d, 0, sizeof(unsigned long long), s.stream));
-            std::vector<int> counts(n_chunks);
-            std::vector<long long> offs(n_chunks);
-            if (n_chunks > 0) {
-                k_tile_count<<<(n_chunks + 127) / 128, 128, 0, s.stream>>>(s.indptr, s.n_rows, counts_d, n_chunks);
-                LAUNCH(h);
-                CU(cudaGetLastError());
-                CU(cudaMemcpyAsync(counts.data(), counts_d, sizeof(int) * n_chunks, cudaMemcpyDeviceToHost, s.stream));
-                CU(cudaStreamSynchronize(s.stream));
-            }
-            long long total = 0;
-            for (int c = 0; c < n_chunks; ++c) { offs[c] = total; total += counts[c]; }
-            s.n_tiles = total;
-            CU(cudaMalloc(&s.tiles, sizeof(Tile) * std::max<long long>(total, 1)));
-            if (n_chunks > 0) {
-                CU(cudaMemcpyAsync(offs_d, offs.data(), sizeof(long long) * n_chunks, cudaMemcpyHostToDevice, s.stream));
-                k_tile_fill<<<(n_chunks + 127) / 128, 128, 0, s.stream>>>(s.indptr, s.n_rows, offs_d, n_chunks, s.tiles, nlong_d);
-                LAUNCH(h);
-                CU(cudaGetLastError());
-            }
-            unsigned long long nl = 0;
-            CU(cudaMemcpyAsync(&nl, nlong_d, sizeof(nl), cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaStreamSynchronize(s.stream));
-            s.n_long = (long long)nl;
-            cudaFree(counts_d); cudaFree(offs_d); cudaFree(nlong_d);
+            int rc = build_tiles(h, s, s.indptr, s.n_rows, &s.tiles, &s.n_tiles, &s.n_long);
+            if (rc) return rc;
         }
         tm.lap("  tiles");
         k_col_signature<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(
@@ -673,6 +840,15 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
     }
     if (tm.on) sync_all(h);
     tm.lap("build Q + row init");
+    if (h->kernel == TSC_KERNEL_ELL) {
+        for (auto& s : h->shards) {
+            CU(cudaSetDevice(s.dev));
+            CU(cudaFuncSetAttribute(k_ell_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEllSmem));
+            int rc = build_ell(h, s);
+            if (rc) return rc;
+        }
+        tm.lap("clustered ELL stream");
+    }
     // totals over all shards (model.py:691-699)
     ALLREDUCE(h, s.scalars, 2, ncclFloat64, ncclSum);
     ALLREDUCE(h, s.scalars + 2, 1, ncclFloat64, ncclMax);
@@ -894,10 +1070,11 @@ extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float
         TileArgs a{};
         a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.K = h->K; a.R = h->R;
         switch (pass_id) {
-            case 0:
-                a.wy = s.wy; a.tab_amb = s.pt; a.acc = s.acc;
-                launch_tiles<TILE_FUSED>(s, a, false);
-                break;
+            case 0: {
+                const int rc0 = launch_fused(h, s, false);
+                if (rc0) err = cudaErrorUnknown;
+                h->launches -= 1;            // counted below
+            } break;
             case 1:
                 a.tab_amb = ta; a.tab_uni = tu; a.z_out = zd;
                 launch_tiles<TILE_Z>(s, a, false);
@@ -941,18 +1118,34 @@ extern "C" int tsc_get_kernel_times(tsc_handle* h, float* ms_out, int32_t max_n,
 }
 
 // ------------------------------------------------------------------------------------------------- EM
-static int launch_fused(tsc_handle* h, Shard& s) {
+static int launch_fused(tsc_handle* h, Shard& s, bool gated) {
+    const EmState* st = gated ? s.st : nullptr;
     if (h->kernel == TSC_KERNEL_ROWS) {
         launch_rows(h->G, [&](auto g) {
-            k_fused_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), s.wy, s.pt, s.acc, h->K, h->R, s.st);
+            k_fused_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), s.wy, s.pt, s.acc, h->K, h->R, st);
         });
+        LAUNCH(h);
+    } else if (h->kernel == TSC_KERNEL_ELL) {
+        // the clustered stream, then whatever does not fit a slice through the flat tiles of the residual CSR
+        if (s.ell_slices > 0) {
+            EllArgs e{s.ell_stream, s.ell_rec_off, s.ell_slices, s.pt, s.acc, h->K, h->R, st};
+            k_ell_fused<<<s.ell_grid, 32, kEllSmem, s.stream>>>(e);
+            LAUNCH(h);
+        }
+        if (s.res_rows > 0) {
+            TileArgs a{};
+            a.tiles = s.res_tiles; a.n_tiles = s.res_n_tiles; a.q = s.res_q; a.col = s.res_col; a.wy = s.res_wy; a.tab_amb = s.pt;
+            a.acc = s.acc; a.K = h->K; a.R = h->R; a.s_cols = 0; a.st = st;
+            launch_tiles<TILE_FUSED>(s, a, false, s.res_n_long * 200 > s.res_n_tiles ? 1 : 0);
+            LAUNCH(h);
+        }
     } else {
         TileArgs a{};
         a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.wy = s.wy; a.tab_amb = s.pt;
-        a.acc = s.acc; a.K = h->K; a.R = h->R; a.s_cols = s.s_cols; a.st = s.st;
+        a.acc = s.acc; a.K = h->K; a.R = h->R; a.s_cols = s.s_cols; a.st = st;
         launch_tiles<TILE_FUSED>(s, a, s.s_cols > 0);
+        LAUNCH(h);
     }
-    LAUNCH(h);
     CU(cudaGetLastError());
     return TSC_OK;
 }
@@ -1027,7 +1220,7 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
         for (auto& s : h->shards) {
             CU(cudaSetDevice(s.dev));
             if (&s == &s0) CU(cudaEventRecord(s0.ev_k[2 * it], s.stream));
-            int rc = launch_fused(h, s);
+            int rc = launch_fused(h, s, true);
             if (rc) return rc;
             if (&s == &s0) CU(cudaEventRecord(s0.ev_k[2 * it + 1], s.stream));
             k_reduce_replicas<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.acc, K, h->R, s.thetasum, s.st);

@@ -281,7 +281,7 @@ __device__ __forceinline__ double row_numerators(const Csr& a, long long s, long
 template <int G>
 __global__ void __launch_bounds__(512) k_fused_rows(Csr a, const double* __restrict__ wy, const double* __restrict__ pt,
                                                     double* __restrict__ acc, int K, int R, const EmState* __restrict__ st) {
-    if (st->done) return;
+    if (st && st->done) return;
     double* my = acc + (size_t)(blockIdx.x % R) * K;
     const unsigned m = group_mask<G>();
     const int lane = threadIdx.x & (G - 1);

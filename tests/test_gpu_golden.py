@@ -38,7 +38,7 @@ def _aligned(z, m):
     return out
 
 
-@pytest.mark.parametrize("kernel", ["tiles", "rows"])
+@pytest.mark.parametrize("kernel", ["ell", "tiles", "rows"])
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
 def test_gpu_matches_reference_golden(path, kernel):
     g = np.load(path)

@@ -96,7 +96,7 @@ def test_single_steps_match_oracle(case):
     tl.close()
 
 
-@pytest.mark.parametrize("kernel", ["rows", "tiles"])
+@pytest.mark.parametrize("kernel", ["rows", "tiles", "ell"])
 @pytest.mark.parametrize("case", CASES)
 def test_em_matches_oracle(case, kernel):
     m = _matrix(**case)
@@ -205,12 +205,13 @@ def test_edge_shapes():
 def test_rows_and_tiles_kernels_agree_at_scale():
     m = _matrix(N=400000, K=5000, avg=20, skew=True, seed=41)
     opts = Opts(max_iter=8, em_epsilon=-1)
-    a, b = _tl(m, opts, kernel="rows"), _tl(m, opts, kernel="tiles")
-    a.em(); b.em()
-    assert a.n_iter == b.n_iter == 8
+    a, b, c = _tl(m, opts, kernel="rows"), _tl(m, opts, kernel="tiles"), _tl(m, opts, kernel="ell")
+    a.em(); b.em(); c.em()
+    assert a.n_iter == b.n_iter == c.n_iter == 8
     assert rel_err(a.pi, b.pi) < 1e-9 and rel_err(a.theta, b.theta) < 1e-9
-    assert abs(a.lnl - b.lnl) <= 1e-10 * abs(a.lnl)
-    a.close(); b.close()
+    assert rel_err(a.pi, c.pi) < 1e-9 and rel_err(a.theta, c.theta) < 1e-9
+    assert abs(a.lnl - b.lnl) <= 1e-10 * abs(a.lnl) and abs(a.lnl - c.lnl) <= 1e-10 * abs(a.lnl)
+    a.close(); b.close(); c.close()
 
 
 def test_multi_gpu_in_process_matches_single():
@@ -307,7 +308,7 @@ def test_config3_size_independent_properties():
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("kernel", ["tiles", "rows"])
+@pytest.mark.parametrize("kernel", ["tiles", "rows", "ell"])
 def test_long_reads_every_path(kernel):
     """Reads of 129..256 entries (single-pass long path), > 256 (two-pass path), exactly 128 (a full regular tile) and
     short ones, interleaved, against the oracle -- fused kernel, posterior export, log-likelihood and reassignment."""
@@ -332,6 +333,79 @@ def test_long_reads_every_path(kernel):
     tl.em(use_likelihood=True); o.em(use_likelihood=True)
     assert tl.n_iter == o.n_iter and abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
     tl.close()
+
+
+def _ell_edge_matrix(K, seed):
+    """Reads that sit on every boundary of the clustered-stream layout (csrc/tsc_ell.cuh): 2 and 48 entries (the
+    slice limits), 49 (one too many -> residual tiles), locus spans of exactly 96 (fits) and 97 (does not), groups of
+    reads with the same first locus (full slices), isolated first loci far apart (slices whose later members are
+    evicted), reads at the last loci (window blocks beyond K), unique reads (skipped), and a long read."""
+    rng = np.random.default_rng(seed)
+    rows = []
+
+    def run(first, n, span=None):
+        span = n - 1 if span is None else span
+        mid = np.sort(rng.choice(np.arange(first + 1, first + span), n - 2, replace=False)) if n > 2 else np.zeros(0, int)
+        return np.concatenate(([first], mid, [first + span])).astype(np.int64)
+
+    for first in (0, 1, 31, 32, 33, 95, 200, 201):
+        for _ in range(40):                                     # many reads per first locus -> full slices
+            n = int(rng.integers(2, 49))
+            rows.append(run(first, n, int(rng.integers(n - 1, 97))))
+    rows.append(run(5, 2, 96)); rows.append(run(5, 2, 97))      # span limit
+    rows.append(run(7, 48, 96)); rows.append(run(7, 49, 96))    # length limit
+    rows.append(run(9, 48, 47)); rows.append(run(9, 2, 1))
+    for first in range(300, K - 100, 37):                       # sparse region: one read per first locus
+        rows.append(run(first, int(rng.integers(2, 30)), int(rng.integers(40, 97))))
+    for _ in range(60):                                         # the last loci of the matrix
+        n = int(rng.integers(2, 20))
+        rows.append(run(K - 1 - 2 * n - int(rng.integers(0, 5)), n, 2 * n))
+    rows.append(np.arange(K - 40, K, dtype=np.int64))           # ends exactly at K-1
+    for _ in range(50):
+        rows.append(np.array([int(rng.integers(0, K))]))        # unique reads
+    rows.append(np.sort(rng.choice(K, 300, replace=False)))     # long read
+    order = rng.permutation(len(rows))
+    rows = [rows[i] for i in order]
+    lens = [len(r) for r in rows]
+    indptr = np.cumsum([0] + lens)
+    indices = np.concatenate(rows).astype(np.int32)
+    raw = (150 + rng.integers(0, 60, indices.size)).astype(np.uint16)
+    return sp.csr_matrix((raw, indices, indptr), shape=(len(rows), K))
+
+
+@pytest.mark.parametrize("K", [700, 400, 1000])
+def test_ell_stream_boundaries(K):
+    m = _ell_edge_matrix(K, 90 + K)
+    opts = Opts(max_iter=8)
+    tl, t2, o = _tl(m, opts, kernel="ell"), _tl(m, opts, kernel="tiles"), _oracle(m, opts)
+    tl.em(); t2.em(); o.em()
+    assert tl.n_iter == o.n_iter
+    assert rel_err(tl.diffs, o.diffs) < RTOL
+    assert rel_err(tl.pi, o.pi) < TIGHT and rel_err(tl.theta, o.theta) < TIGHT
+    assert rel_err(tl.pi, t2.pi) < TIGHT
+    assert abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
+    for method in ("exclude", "unique", "all"):
+        assert np.array_equal(tl.reassign_colsum(method), o.reassign_colsum(method))
+    tl.close(); t2.close()
+
+
+def test_ell_handles_unsorted_columns_through_the_residual_path():
+    """Non-canonical CSR (loci not increasing inside a read) must not enter a slice: the stream relies on distinct,
+    increasing loci per read."""
+    rng = np.random.default_rng(5)
+    K, N = 300, 4000
+    lens = rng.integers(1, 12, N)
+    rows = [rng.choice(np.arange(max(0, f - 20), min(K, f + 20)), n, replace=False) for f, n in zip(rng.integers(0, K, N), lens)]
+    indptr = np.cumsum(np.concatenate(([0], lens)))
+    indices = np.concatenate(rows).astype(np.int32)
+    raw = (150 + rng.integers(0, 60, indices.size)).astype(np.uint16)
+    m = sp.csr_matrix((raw, indices, indptr), shape=(N, K))        # scipy keeps the order it is given
+    assert not m.has_sorted_indices
+    opts = Opts(max_iter=5)
+    a, b = _tl(m, opts, kernel="ell"), _tl(m, opts, kernel="rows")
+    a.em(); b.em()
+    assert rel_err(a.pi, b.pi) < TIGHT and abs(a.lnl - b.lnl) <= TIGHT * abs(b.lnl)
+    a.close(); b.close()
 
 
 @pytest.mark.parametrize("kw", [dict(permute_columns=True), dict(smem_table_cols=64), dict(smem_table_cols=10 ** 6),

@@ -320,6 +320,11 @@ def main():
     alg_bytes = local_nnz * 12.0 + (rows_local + 1) * 4.0
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     traffic = ncu_traffic(local_nnz)
+    layout = tl.layout_stats()
+    fused_name = ("k_ell_fused (E-step + M-step accumulation over the clustered slice stream, telescope_b200/csrc/tsc_ell.cuh)"
+                  + (" + k_tiles<TILE_FUSED> on the residual CSR" if layout["residual_reads"] else "")
+                  if layout["slices"] else
+                  "k_tiles<TILE_FUSED> (E-step + M-step accumulation, telescope_b200/csrc/tsc_tiles.cuh)")
 
     line = None
     if rank == 0:
@@ -347,10 +352,11 @@ def main():
             "gpu_launches": c1["launches"] - c0["launches"],
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_tiles<TILE_FUSED> (E-step + M-step accumulation, telescope_b200/csrc/tsc_tiles.cuh)",
+                "traffic": traffic, "kernel": fused_name,
                 "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
             },
             "final_lnl": tl.lnl,
+            "layout": layout,
             "other_kernels": {
                 "estep_z": None if not passes.get("estep") else {
                     "ms": passes["estep"], "algorithmic_bytes": local_nnz * 20.0 + (rows_local + 1) * 4.0,

@@ -136,7 +136,7 @@ struct Shard {
     // clustered sliced-ELL stream of the fused kernel (tsc_ell.cuh) + residual CSR for the reads it does not hold
     unsigned char* ell_stream = nullptr;
     long long ell_bytes = 0, ell_slices = 0, ell_reads = 0, ell_entries = 0;
-    long long* ell_rec_off = nullptr;     // ell_slices + 1 record offsets
+    int4* ell_index = nullptr;            // per slice record: offset / 16, first locus, T | last locus << 8, reads
     int ell_grid = 0;
     long long res_rows = 0, res_nnz = 0, res_n_tiles = 0, res_n_long = 0;
     long long* res_indptr = nullptr;
@@ -292,7 +292,7 @@ static void free_shard(Shard& s) {
     void* ptrs[] = {s.indptr, s.col, s.q, s.wy, s.tiles, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
                     s.pi_init, s.theta_init, s.pisum0, s.acc, s.thetasum, s.ones, s.tmp_a, s.tmp_b, s.tmp_c, s.colsum,
                     s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad,
-                    s.ell_stream, s.ell_rec_off, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles};
+                    s.ell_stream, s.ell_index, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.st_host) cudaFreeHost(s.st_host);
     for (auto& e : s.ev_poll) if (e) cudaEventDestroy(e);
@@ -489,13 +489,14 @@ static int build_ell(tsc_handle* h, Shard& s) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ell_fused, 32, kEllSmem));
         const int warps = s.n_sm * std::max(per_sm, 1);
         const long long n_seg = (n_slices + 31) / 32;      // a warp's unit of work between two window flushes
+        if (total >= (1LL << 36)) return fail(TSC_ERR_ARG, "slice stream of one GPU exceeds 64 GB");
         CU(cudaMalloc(&s.ell_stream, (size_t)total));
         k_ell_fill<<<grid_for(n_slices * 32, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, s.col, s.q, s.wy, sorted, n_cand, n_slices,
                                                                                    hdr, rec_off, s.ell_stream);
         LAUNCH(h);
         CU(cudaGetLastError());
-        s.ell_rec_off = rec_off;               // kept: the kernel's record index
-        tmp.p.erase(std::find(tmp.p.begin(), tmp.p.end(), (void*)rec_off));
+        s.ell_index = hdr;                     // kept: the kernel's record index
+        tmp.p.erase(std::find(tmp.p.begin(), tmp.p.end(), (void*)hdr));
         CU(cudaStreamSynchronize(s.stream));
         s.ell_bytes = total;
         s.ell_slices = n_slices;
@@ -537,7 +538,24 @@ static int build_ell(tsc_handle* h, Shard& s) {
             if (rc) return rc;
         }
     }
-    s.ell_reads = n_cand;     // before eviction; the exact split is res_rows / res_nnz
+    {   // reads / entries that made it into the stream = ambiguous - residual
+        DevBuf t2;
+        int *flag = nullptr, *rlen = nullptr;
+        long long* pos = nullptr;
+        CU(t2.alloc(&flag, n_rows));
+        CU(t2.alloc(&rlen, n_rows));
+        CU(t2.alloc(&pos, (size_t)n_rows + 1));
+        k_res_flags<<<grid_for(n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, nullptr, flag, rlen);
+        LAUNCH(h);
+        long long amb_rows = 0, amb_nnz = 0;
+        int rc = device_scan<int>(h, s, flag, n_rows, pos);
+        if (!rc) rc = fetch_ll(s, pos + n_rows, &amb_rows);
+        if (!rc) rc = device_scan<int>(h, s, rlen, n_rows, pos);
+        if (!rc) rc = fetch_ll(s, pos + n_rows, &amb_nnz);
+        if (rc) return rc;
+        s.ell_reads = amb_rows - s.res_rows;
+        s.ell_entries = amb_nnz - s.res_nnz;
+    }
     CU(cudaStreamSynchronize(s.stream));
     return TSC_OK;
 }
@@ -1017,6 +1035,14 @@ extern "C" int tsc_get_counters(tsc_handle* h, int64_t* launches, int64_t* h2d_b
     return TSC_OK;
 }
 
+extern "C" int tsc_get_layout_stats(tsc_handle* h, int64_t* out8) {
+    if (!h || !out8) return fail(TSC_ERR_ARG, "NULL argument");
+    const Shard& s = h->shards[0];
+    out8[0] = s.ell_bytes; out8[1] = s.ell_slices; out8[2] = s.ell_reads; out8[3] = s.ell_entries;
+    out8[4] = s.res_rows; out8[5] = s.res_nnz; out8[6] = s.ell_grid; out8[7] = s.n_tiles;
+    return TSC_OK;
+}
+
 extern "C" int tsc_get_em_device_ms(tsc_handle* h, float* ms_out) {
     if (!h || !ms_out) return fail(TSC_ERR_ARG, "NULL argument");
     *ms_out = h->em_ms;
@@ -1128,7 +1154,7 @@ static int launch_fused(tsc_handle* h, Shard& s, bool gated) {
     } else if (h->kernel == TSC_KERNEL_ELL) {
         // the clustered stream, then whatever does not fit a slice through the flat tiles of the residual CSR
         if (s.ell_slices > 0) {
-            EllArgs e{s.ell_stream, s.ell_rec_off, s.ell_slices, s.pt, s.acc, h->K, h->R, st};
+            EllArgs e{s.ell_stream, s.ell_index, s.ell_slices, s.pt, s.acc, h->K, h->R, st};
             k_ell_fused<<<s.ell_grid, 32, kEllSmem, s.stream>>>(e);
             LAUNCH(h);
         }

@@ -14,16 +14,19 @@
 //     atomics at all in the loop.  A window block is flushed (16 copies summed in fixed order, one coalesced
 //     RED.ADD.F64 of 32 doubles) only when the sorted stream has moved past it: a few thousand sector REDs per
 //     iteration instead of 5e8.
-// The slice records form one byte stream in HBM; a warp takes segments of 32 consecutive records and pulls every record
-// with ONE 1-D TMA bulk copy (cp.async.bulk + mbarrier complete_tx) into a 12 KB shared-memory ring, several records
-// ahead of the arithmetic, so 7 one-warp CTAs per SM keep enough bytes in flight for the HBM roofline with no load
-// instruction on the global path.
+// The slice records form one byte stream in HBM; a warp takes segments of 32 consecutive records.  It asks the TMA
+// unit to pull each record into L2 several records ahead (cp.async.bulk.prefetch.L2, one instruction per record) and
+// then loads the record's loci / Q straight into registers -- every load of a slice is in flight at once, all of them
+// L2 hits.  (A first version staged the records in a shared-memory ring with cp.async.bulk + mbarrier; ncu showed the
+// shared-memory pipe ~75 % busy because the Q stream crossed it twice, TMA write + LDS, and the 12 KB ring capped the
+// SM at 7 warps; see profiles/r2_ell_kernel_ncu_summary.md.)  With 17.6 KB of window per one-warp CTA, 12 warps per
+// SM hide the L2 latency.
 //
-// Record (16-byte aligned, 144 + 288*T bytes):
-//   int32 lo, T, hi, n_reads | double wy[16] | uint8 wcol[T][32] | double q[T][32]
+// Record (16-byte aligned, 128 + 288*T bytes):  double wy[16] | uint8 wcol[T][32] | double q[T][32]
+// Index (16 bytes per record): byte offset / 16, first locus lo, T | last locus << 8.
 // wcol = locus & 127, the entry's row in the window (blocks of 32 loci live in slot (locus >> 5) & 3), or 128 for an
 // empty slot: the dummy row, with q = 0 and pi*theta = 0, so empty slots add an exact +0.0 to a word nobody reads.
-// With one byte per locus the stream moves ~9.4 B per entry where canonical CSR moves 12.
+// With one byte per locus the stream moves ~9.5 B per entry where canonical CSR moves 12.
 //
 // Reads that do not fit a slice (fewer than 2 or more than 2*kEllTMax entries, a locus span above kEllSpan, or
 // non-increasing loci) are not in the stream: unique reads add nothing to the M-step sums (model.py:730-733; they
@@ -37,14 +40,16 @@ constexpr int kEllReads = 16;                 // reads per slice
 constexpr int kEllTMax = 24;                  // steps per slice; a read holds at most 2*kEllTMax entries
 constexpr int kEllWin = 128;                  // loci in a warp's window (4 blocks of 32)
 constexpr int kEllSpan = 96;                  // max (locus - slice lo) inside a slice; lo % 32 + span < kEllWin
-constexpr int kEllHdr = 16 + kEllReads * 8;   // header + wy
-constexpr int kEllRing = 12288;               // bytes of record ring per warp (a record is 144 + 288*T <= 7056 bytes)
-constexpr int kEllQueue = 8;                  // records in flight per warp (mbarrier slots)
+constexpr int kEllHdr = kEllReads * 8;        // wy
+#ifndef TSC_ELL_AHEAD
+#define TSC_ELL_AHEAD 6
+#endif
+constexpr int kEllAhead = TSC_ELL_AHEAD;      // records between the L2 prefetch and the loads
 constexpr int kEllLenBits = 6;                // sort key = first locus << 6 | snake(length)
-constexpr size_t kEllSmem = kEllRing + sizeof(double) * ((kEllWin + 1) * kEllReads + kEllWin + 8) + 8 * kEllQueue + 4 * kEllQueue;
+constexpr size_t kEllSmem = sizeof(double) * ((kEllWin + 1) * kEllReads + kEllWin + 8);
 static_assert(2 * kEllTMax < (1 << kEllLenBits), "length must fit the key");
 static_assert(kEllTMax == 24, "k_ell_fused dispatches bodies of 4..24 steps");
-static_assert(kEllHdr + 288 * kEllTMax <= kEllRing, "the largest record must fit the ring");
+static_assert(kEllAhead >= 1 && kEllAhead < 32, "prefetch distance is within one segment");
 
 __host__ __device__ inline int ell_record_bytes(int T) { return kEllHdr + 288 * T; }
 
@@ -184,31 +189,33 @@ __global__ void k_ell_slices(const long long* __restrict__ ip, const int* __rest
             T = max(T, (int)((e - b + 1) >> 1));
             ++kept;
         }
-        hdr[s] = make_int4(lo, T, hi, kept);
+        hdr[s] = make_int4(0, lo, T | (hi << 8), kept);
         rec_bytes[s] = ell_record_bytes(T);
     }
 }
 
-// One warp per slice writes its record.
+// One warp per slice writes its record and completes its index entry.
 __global__ void __launch_bounds__(256) k_ell_fill(const long long* __restrict__ ip, const int* __restrict__ col,
                                                   const double* __restrict__ q, const double* __restrict__ wy,
                                                   const int* __restrict__ sorted, long long n_cand, long long n_slices,
-                                                  const int4* __restrict__ hdr, const long long* __restrict__ rec_off,
+                                                  int4* __restrict__ hdr, const long long* __restrict__ rec_off,
                                                   unsigned char* __restrict__ stream) {
     const int lane = threadIdx.x & 31, r = lane & 15, h = lane >> 4;
     long long s = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
     for (; s < n_slices; s += stride) {
         const int4 hd = hdr[s];
-        unsigned char* rec = stream + rec_off[s];
-        if (lane == 0) *reinterpret_cast<int4*>(rec) = hd;
+        const long long off = rec_off[s];
+        unsigned char* rec = stream + off;
+        __syncwarp();
+        if (lane == 0) hdr[s].x = (int)(off >> 4);
         const long long p = s * kEllReads + r;
         const int read = (p < n_cand) ? sorted[p] : -1;
         long long b = 0;
         int len = 0;
         if (read >= 0) { b = ip[read]; len = (int)(ip[read + 1] - b); }
-        if (h == 0) reinterpret_cast<double*>(rec + 16)[r] = (read >= 0) ? wy[read] : 0.0;
-        const int T = hd.y;
+        if (h == 0) reinterpret_cast<double*>(rec)[r] = (read >= 0) ? wy[read] : 0.0;
+        const int T = hd.z & 0xff;
         unsigned char* dc = rec + kEllHdr;
         double* qq = reinterpret_cast<double*>(rec + kEllHdr + 32 * T);
         for (int t = 0; t < T; ++t) {
@@ -255,30 +262,9 @@ __global__ void __launch_bounds__(256) k_res_copy(const long long* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------------
 // the per-iteration kernel
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned ell_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ell_mbar_init(unsigned bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void ell_mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ell_bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void ell_mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "ELL_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra ELL_DONE;\n\t"
-        "bra ELL_WAIT;\n\t"
-        "ELL_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-
 struct EllArgs {
     const unsigned char* stream;
-    const long long* rec_off;     // n_slices + 1 byte offsets of the slice records
+    const int4* index;            // per record: byte offset / 16, lo, T | hi << 8, reads
     long long n_slices;
     const double* pt;             // pi*theta
     double* acc;                  // R replicas of K doubles
@@ -286,30 +272,43 @@ struct EllArgs {
     const EmState* st;            // nullptr = always run
 };
 
-// One slice record, TM = T rounded up to a multiple of 4: straight-line code, every load of the slice can be in flight
-// at once; only the last three steps are conditional.
+__device__ __forceinline__ void ell_prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ double ell_ld_stream(const double* p) {      // read once: do not keep it in L1
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// One slice record, TM = T rounded up to a multiple of 4: straight-line code, every load of the slice is in flight at
+// once; only the last three steps are conditional.
 template <int TM>
-__device__ __forceinline__ void ell_body(const unsigned char* rec, int T, int lane, const double* s_pt,
+__device__ __forceinline__ void ell_body(const unsigned char* __restrict__ rec, int T, int lane, const double* s_pt,
                                          unsigned char* accb /* s_acc + 8 * (lane & 15) */) {
-    const double w_mine = reinterpret_cast<const double*>(rec + 16)[lane & 15];
+    const double w_mine = __ldg(reinterpret_cast<const double*>(rec) + (lane & 15));
     const unsigned char* cp = rec + kEllHdr + lane;
     const double* qp = reinterpret_cast<const double*>(rec + kEllHdr + 32 * T) + lane;
     double n[TM];
-    unsigned ao[TM];              // byte offset of the entry's accumulator row
-    double s0 = 0.0, s1 = 0.0;
-    // ---- pass 1: numerators n = Q * (pi*theta)[locus], private row sum
+    unsigned ao[TM];              // window row of the entry, then byte offset of its accumulator row
 #pragma unroll
     for (int t = 0; t < TM; ++t) {
         n[t] = 0.0;
-        ao[t] = kEllWin * kEllReads * 8;            // dummy row
+        ao[t] = kEllWin;                              // dummy row
         if (t < TM - 3 || t < T) {
-            const unsigned jw = cp[32 * t];
-            ao[t] = jw * (kEllReads * 8);
-            n[t] = qp[32 * t] * s_pt[jw];
-            if (t & 1) s1 += n[t]; else s0 += n[t];
+            ao[t] = __ldg(cp + 32 * t);
+            n[t] = ell_ld_stream(qp + 32 * t);
         }
     }
-    double sum = s0 + s1;
+    // ---- pass 1: numerators n = Q * (pi*theta)[locus], private row sum
+    double sp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int t = 0; t < TM; ++t) {
+        n[t] *= s_pt[ao[t]];
+        sp[t & 3] += n[t];
+        ao[t] *= kEllReads * 8;
+    }
+    double sum = (sp[0] + sp[1]) + (sp[2] + sp[3]);
     sum += __shfl_xor_sync(0xffffffffu, sum, 16);
     // (w*Y) * recip0(total), the same expression as the tile kernel; empty read slots have w = 0
     const double g = (w_mine != 0.0) ? w_mine * recip0(sum) : 0.0;
@@ -325,49 +324,34 @@ __device__ __forceinline__ void ell_body(const unsigned char* rec, int T, int la
 __global__ void __launch_bounds__(32) k_ell_fused(const EllArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     if (a.st && a.st->done) return;
-    unsigned char* ring = s_raw;
-    double* s_acc = reinterpret_cast<double*>(s_raw + kEllRing);          // [kEllWin + 1][kEllReads]; last row = dummy
+    double* s_acc = reinterpret_cast<double*>(s_raw);                     // [kEllWin + 1][kEllReads]; last row = dummy
     double* s_pt = s_acc + (kEllWin + 1) * kEllReads;                    // [kEllWin + 8]; [kEllWin] = 0 for empty slots
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_pt + kEllWin + 8);
-    int* s_rpos = reinterpret_cast<int*>(s_bar + kEllQueue);
     const int lane = threadIdx.x;
-    const int K = a.K;
-    const double* __restrict__ pt = a.pt;
-    double* my = a.acc + (size_t)(blockIdx.x % a.R) * K;
-    const unsigned ring_u32 = ell_smem_u32(ring), bar_u32 = ell_smem_u32(s_bar);
-    unsigned char* accb = reinterpret_cast<unsigned char*>(s_acc) + 8 * (lane & 15);
-
-    for (int i = lane; i < (kEllWin + 1) * kEllReads + kEllWin + 8; i += 32) s_acc[i] = 0.0;     // accumulators and s_pt
-    if (lane == 0) {
-        for (int i = 0; i < kEllQueue; ++i) ell_mbar_init(bar_u32 + 8 * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncwarp();
-
     const int nw = gridDim.x;
     const long long n_slices = a.n_slices;
     const int n_seg = (int)((n_slices + 31) >> 5);            // a segment = 32 consecutive records
-    // lane l of a segment's register set holds record 32*seg + l: byte offset and size
-    auto load_seg = [&](int seg, long long& off, int& sz, int& count) {
-        off = 0; sz = 0; count = 0;
+    const int K = a.K;
+    const double* __restrict__ pt = a.pt;
+    const unsigned char* __restrict__ stream = a.stream;
+    double* my = a.acc + (size_t)(blockIdx.x % a.R) * K;
+    unsigned char* accb = reinterpret_cast<unsigned char*>(s_acc) + 8 * (lane & 15);
+
+    for (int i = lane; i < (kEllWin + 1) * kEllReads + kEllWin + 8; i += 32) s_acc[i] = 0.0;     // accumulators, s_pt
+    __syncwarp();
+
+    // lane l of a segment's index registers describes record 32*seg + l (T = 0 beyond the end)
+    auto load_seg = [&](int seg) -> int4 {
+        int4 v = make_int4(0, 0, 0, 0);
         if (seg < n_seg) {
             const long long idx = ((long long)seg << 5) + lane;
-            count = (int)min(32LL, n_slices - ((long long)seg << 5));
-            if (idx < n_slices) { off = a.rec_off[idx]; sz = (int)(a.rec_off[idx + 1] - off); }
+            if (idx < n_slices) v = __ldg(a.index + idx);
         }
+        return v;
     };
-    // ---- producer state (tracked by every lane, issued by lane 0): the next record to request
-    int prec = 0, pcount, ncount;
-    long long poff, noff;
-    int psz, nsz;
-    load_seg(blockIdx.x, poff, psz, pcount);
-    load_seg(blockIdx.x + nw, noff, nsz, ncount);
-    int pnext_seg = blockIdx.x + 2 * nw;
-    unsigned issued = 0, consumed = 0;                // records, per warp
-    int head = 0, tail = 0;                           // ring allocator: in-flight records occupy [tail .. head) in FIFO order
-    int Fb = -1;                                      // first block (32 loci) of the window; -1 = empty
-
+    auto prefetch_mine = [&](const int4& v) {          // this lane's record -> L2
+        const int T = v.z & 0xff;
+        if (T) ell_prefetch_l2(stream + ((long long)(unsigned)v.x << 4), (unsigned)ell_record_bytes(T));
+    };
     auto flush_block = [&](int b) {
         const int row = ((b & 3) * 32 + lane) * kEllReads;
         double s = 0.0;
@@ -379,40 +363,24 @@ __global__ void __launch_bounds__(32) k_ell_fused(const EllArgs a) {
         if (j < K && s != 0.0) atomicAdd(my + j, s);
     };
 
+    int4 cur = load_seg(blockIdx.x), nxt = load_seg(blockIdx.x + nw);
+    if (lane < kEllAhead) prefetch_mine(cur);         // the first records of the first segment
+    int Fb = -1;                                      // first block (32 loci) of the window; -1 = empty
+
     for (int seg = blockIdx.x; seg < n_seg; seg += nw) {
+        const int4 after = load_seg(seg + 2 * nw);    // requested two segments early
         const int nrec = (int)min(32LL, n_slices - ((long long)seg << 5));
         for (int c = 0; c < nrec; ++c) {
-            // ---- everything before the current record is free; keep the ring full
-            __syncwarp();
-            if (issued == consumed) { head = 0; tail = 0; }
-            else tail = s_rpos[consumed % kEllQueue];
-            while (issued - consumed < kEllQueue - 1 && pcount > 0) {
-                const int S = __shfl_sync(0xffffffffu, psz, prec);
-                int place;
-                if (issued == consumed) place = 0;
-                else if (head > tail) { place = (kEllRing - head >= S) ? head : ((S <= tail) ? 0 : -1); }
-                else place = (tail - head >= S) ? head : -1;
-                if (place < 0) break;
-                const long long O = __shfl_sync(0xffffffffu, poff, prec);
-                if (lane == 0) {
-                    const unsigned slot = issued % kEllQueue;
-                    s_rpos[slot] = place;
-                    ell_mbar_expect_tx(bar_u32 + 8 * slot, (unsigned)S);
-                    ell_bulk_load(ring_u32 + place, a.stream + O, (unsigned)S, bar_u32 + 8 * slot);
-                }
-                head = place + S;
-                ++issued;
-                if (++prec == pcount) {
-                    poff = noff; psz = nsz; pcount = ncount; prec = 0;
-                    load_seg(pnext_seg, noff, nsz, ncount);
-                    pnext_seg += nw;
-                }
+            // ---- the lane that owns record c + kEllAhead (of this segment or the next) sends it to L2
+            {
+                const int pc = c + kEllAhead;
+                if (lane == (pc & 31)) prefetch_mine(pc < 32 ? cur : nxt);
             }
-            // ---- wait for the current record (an empty ring put it at 0)
-            ell_mbar_wait(bar_u32 + 8 * (consumed % kEllQueue), (consumed / kEllQueue) & 1u);
-            const unsigned char* rec = ring + tail;
-            const int4 hd = *reinterpret_cast<const int4*>(rec);
-            const int lo = hd.x, T = hd.y, hi = hd.z;
+            const unsigned off16 = (unsigned)__shfl_sync(0xffffffffu, cur.x, c);
+            const int lo = __shfl_sync(0xffffffffu, cur.y, c);
+            const int thi = __shfl_sync(0xffffffffu, cur.z, c);
+            const int T = thi & 0xff, hi = thi >> 8;
+            const unsigned char* rec = stream + ((long long)off16 << 4);
 
             // ---- window: blocks [Fb, Fb+4) of 32 loci; the stream is sorted by lo, so it only moves forward
             const int lb = lo >> 5;
@@ -439,8 +407,9 @@ __global__ void __launch_bounds__(32) k_ell_fused(const EllArgs a) {
                 case 5: ell_body<20>(rec, T, lane, s_pt, accb); break;
                 default: ell_body<24>(rec, T, lane, s_pt, accb); break;
             }
-            ++consumed;
         }
+        cur = nxt;
+        nxt = after;
         // ---- segment done: hand the window to the global accumulator
         __syncwarp();
         if (Fb >= 0) for (int b = Fb; b < Fb + 4; ++b) flush_block(b);

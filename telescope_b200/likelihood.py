@@ -295,6 +295,14 @@ class TelescopeLikelihood(object):
         _abi.check(self._lib.tsc_time_pass(self._h, {"fused": 0, "estep": 1, "lnl": 2, "reassign": 3}[which], reps, C.byref(ms)))
         return ms.value
 
+    def layout_stats(self):
+        """Device layout of local shard 0 (diagnostic): the clustered slice stream and the residual CSR."""
+        buf = (C.c_int64 * 8)()
+        _abi.check(self._lib.tsc_get_layout_stats(self._h, buf))
+        names = ("stream_bytes", "slices", "stream_reads", "stream_entries", "residual_reads", "residual_entries",
+                 "stream_ctas", "tiles")
+        return dict(zip(names, (int(v) for v in buf)))
+
     def counters(self):
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         _abi.check(self._lib.tsc_get_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))

@@ -10,15 +10,22 @@ BASELINE.json's metric is quoted on; with N GPUs the same matrix is row-sharded 
 EM iteration (E-step + M-step + parameter update) over the whole matrix; em_epsilon = -1 keeps the loop from
 stopping early, exactly as on the CPU arm.
 
-  value  = K / device time of `em(max_iter=K)` (CUDA events on the library's stream, max over ranks), inputs
-           resident in HBM.  Like the reference's em(), the call ends with one calculate_lnl pass (model.py:800-801).
-  e2e    = K / wall time of the whole job through the public class with HOST (pinned) CSR buffers:
-           TelescopeLikelihood(csr, opts) [H2D of the CSR, Q build, tiling] + em(K) + D2H of pi/theta.
-  roofline = fused E+M kernel: algorithmic bytes nnz*12 + (N+1)*4 / mean per-iteration kernel time
-           measured with CUDA events inside tsc_em, against MEASURED_PEAKS.json's HBM copy bandwidth.
-  cpu_baseline = the scipy.sparse port of the reference loop (oracle/em_scipy.py; op-for-op the reference's calls,
-           single-threaded like scipy) on the first rows of the same matrix, scaled linearly in nnz to the full
-           workload (the reference needs ~100 B/nnz of host RAM; linearity measured in BASELINE.md).
+  value    = K / device time of `em(max_iter=K)` (CUDA events on the library's stream, max over ranks), inputs
+             resident in HBM.  Like the reference's em(), the call ends with one calculate_lnl pass (model.py:800-801).
+  e2e      = K / wall time of the whole job through the public class with HOST (pinned) CSR buffers:
+             TelescopeLikelihood(csr, opts) [H2D of the CSR, Q build, clustering] + em(K) + D2H of pi/theta.
+             e2e_pageable = the same from ordinary (pageable) numpy/scipy arrays, e2e_report = e2e plus the one-pass
+             output_report column sums (model.py:432-458).
+  roofline = the fused E+M kernel(s) of one iteration: ALGORITHMIC bytes nnz*12 + (N+1)*4 / mean
+             per-iteration kernel time (CUDA events inside tsc_em), against MEASURED_PEAKS.json's HBM copy bandwidth;
+             `traffic` = DRAM bytes one launch really moves (ncu capture, profiles/) -- the clustered stream stores a
+             locus in 1 byte and skips unique reads, so it is BELOW the algorithmic bytes; `frac_dram` is the fraction
+             on those real bytes.
+  parity   = every rank feeds the first rows of its block to a second N-rank model; rank 0 runs the CPU oracle
+             (oracle/em_numpy.py) on the concatenated sample: lnl, pi, theta to 1e-6, `exclude` counts bit-exact.
+  other_configs.zipf = BASELINE.json config 5 (Zipf rows, max 200 entries/read): value, fused fraction, parity.
+  cpu_baseline = the UNMODIFIED reference class (oracle/_ref, staged by oracle/make_ref.py; the scipy port when it
+             is absent) on the first 4 % of the reads, single-threaded like scipy, scaled linearly in entries.
 
 `--impl reference` prints the same line for the CPU arm alone (rank 0 only).
 """
@@ -39,6 +46,7 @@ sys.path.insert(0, ROOT)
 METRIC = "em_iterations_per_sec"
 UNIT = "iter/s"
 SEED = 1004
+CPU_SAMPLE_FRACTION = 0.04         # of the reads, for both CPU legs (cpu_baseline and --impl reference)
 
 
 class Opts(object):
@@ -58,19 +66,15 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=50_000_000)
     ap.add_argument("--loci", type=int, default=30_000)
     ap.add_argument("--avg", type=int, default=20)
-    ap.add_argument("--skew", action="store_true", help="config 5: Zipf reads-per-row (max 200)")
+    ap.add_argument("--skew", action="store_true", help="config 5 as the main workload: Zipf reads-per-row (max 200)")
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--replicas", type=int, default=0)
-    ap.add_argument("--smem-table-cols", type=int, default=-1)
-    ap.add_argument("--cpu-seconds", type=float, default=25.0, help="CPU baseline budget")
+    ap.add_argument("--transport", default="nccl", choices=["peer", "nccl"])
+    ap.add_argument("--cpu-seconds", type=float, default=170.0, help="--impl reference: CPU budget for W+K iterations")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip pageable e2e, parity and the Zipf configuration")
     ap.add_argument("--permute", action="store_true", help="renumber loci by descending entry count on the device")
     return ap.parse_args()
-
-
-def workload_name(a):
-    return "synthetic CSR %s reads x %s loci, avg %d alignments/read%s, seed %d" % (
-        _si(a.reads), _si(a.loci), a.avg, ", Zipf rows (max 200)" if a.skew else "", SEED)
 
 
 def _si(n):
@@ -80,45 +84,94 @@ def _si(n):
     return str(n)
 
 
-# ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample_rows(a, n_iters):
-    """Rows of the workload the CPU arm can finish in the budget (reference: ~153 ns per nnz per iteration, +init)."""
-    per_row = 160e-9 * a.avg * (n_iters + 1.5)
-    return int(max(20_000, min(a.reads, a.cpu_seconds / per_row)))
+def workload_name(a, skew=None):
+    skew = a.skew if skew is None else skew
+    return "synthetic CSR %s reads x %s loci, avg %d alignments/read%s, seed %d" % (
+        _si(a.reads), _si(a.loci), a.avg, ", Zipf rows (max 200)" if skew else "", SEED)
 
 
-def run_cpu(a, n_warm, n_iters, csr=None):
-    """Time the scipy port on a bounded sample; returns dict(value=iter/s scaled to the full workload, ...)."""
-    import scipy.sparse as sp
-    from oracle.em_scipy import ScipyEM
-    from telescope_b200.synthetic import synth_csr
-    rows = cpu_sample_rows(a, n_warm + n_iters)
-    if csr is None:
-        ip, ix, raw = synth_csr(a.reads, a.loci, a.avg, a.skew, SEED, 0, rows)
-    else:
-        ip, ix, raw = csr
-        ip = ip[:rows + 1]
-        ix, raw = ix[:ip[-1]], raw[:ip[-1]]
-    m = sp.csr_matrix((np.asarray(raw), np.asarray(ix), np.asarray(ip)), shape=(rows, a.loci))
-    full_nnz = a.reads * float(m.nnz) / rows          # the generator's rows are i.i.d.
-    em = ScipyEM(m, em_epsilon=-1.0, max_iter=max(1, n_warm))
-    if n_warm > 0:
-        em.em()
-    em.max_iter = n_iters
-    t0 = time.perf_counter()
-    em.em()
-    dt = time.perf_counter() - t0
-    sample_ips = n_iters / dt
+def base_config(a, world, total_nnz, alg_bytes_per_gpu):
+    """The part of `config` both arms print identically."""
     return {
-        "value": sample_ips * m.nnz / full_nnz,
+        "workload": workload_name(a), "n_reads": a.reads, "n_loci": a.loci, "nnz": int(total_nnz),
+        "parallelism": ("read-sharded x%d, one exchange of K doubles per iteration" % world) if world > 1 else "1 GPU",
+        "l2": "per-iteration inputs (%.1f GB per GPU) are larger than L2, no flush needed" % (alg_bytes_per_gpu / 1e9),
+    }
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_engine():
+    """('reference', factory) with the unmodified reference class when it is importable, else ('port', factory)."""
+    from oracle import ref_shim
+    if ref_shim.reference_available():
+        model, csr_plus = ref_shim.import_reference()
+        import logging as lg
+
+        class RefRun(object):
+            def __init__(self, m, max_iter):
+                self.tl = model.TelescopeLikelihood(csr_plus(m), ref_shim.RefOpts(em_epsilon=-1.0, max_iter=max_iter))
+
+            def em(self, n):
+                self.tl.max_iter = n
+                self.tl.em(use_likelihood=False, loglev=lg.DEBUG)
+                return self
+
+            lnl = property(lambda self: float(self.tl.lnl))
+            pi = property(lambda self: np.asarray(self.tl.pi))
+            theta = property(lambda self: np.asarray(self.tl.theta))
+        where = "oracle/_ref (staged copy)" if ref_shim.reference_is_staged_copy() else ref_shim.REFERENCE_ROOT
+        return "reference", RefRun, "telescope.utils.model.TelescopeLikelihood, unmodified, from " + where
+    from oracle.em_scipy import ScipyEM
+
+    class PortRun(object):
+        def __init__(self, m, max_iter):
+            self.o = ScipyEM(m, em_epsilon=-1.0, max_iter=max_iter)
+
+        def em(self, n):
+            self.o.max_iter = n
+            self.o.em()
+            return self
+
+        lnl = property(lambda self: float(self.o.lnl))
+        pi = property(lambda self: np.asarray(self.o.pi))
+        theta = property(lambda self: np.asarray(self.o.theta))
+    return "port", PortRun, "oracle/em_scipy.py (op-for-op scipy port; the staged reference is missing)"
+
+
+def cpu_sample_rows(a, n_iters=None, budget_s=None):
+    rows = int(max(20_000, min(a.reads, round(a.reads * CPU_SAMPLE_FRACTION))))
+    if n_iters and budget_s:       # keep W+K iterations inside the budget (~180 ns per entry and iteration + init)
+        rows = int(min(rows, max(20_000, budget_s / (180e-9 * a.avg * (n_iters + 2.0)))))
+    return rows
+
+
+def run_cpu(a, n_warm, n_iters, rows, full_nnz):
+    """Time the CPU implementation on the first `rows` reads; value = iter/s scaled linearly to the full workload."""
+    import scipy.sparse as sp
+    from telescope_b200.synthetic import synth_csr
+    kind, Run, what = cpu_engine()
+    ip, ix, raw = synth_csr(a.reads, a.loci, a.avg, a.skew, SEED, 0, rows)
+    m = sp.csr_matrix((np.asarray(raw), np.asarray(ix), np.asarray(ip)), shape=(rows, a.loci))
+    t0 = time.perf_counter()
+    run = Run(m, max(1, n_warm))
+    t_init = time.perf_counter() - t0
+    if n_warm > 0:
+        run.em(n_warm)
+    t0 = time.perf_counter()
+    run.em(n_iters)
+    dt = time.perf_counter() - t0
+    return {
+        "value": (n_iters / dt) * m.nnz / full_nnz,
         "unit": UNIT,
         "cores": 1,
-        "kind": "port",
-        "sample": "first %d reads (%d entries, %.3g of the workload), %d timed EM iterations in %.1f s = %.1f ns/entry/iter; "
-                  "scaled linearly in entries to the full matrix" % (rows, m.nnz, m.nnz / full_nnz, n_iters, dt,
-                                                                     dt / n_iters / m.nnz * 1e9),
+        "kind": kind,
+        "sample": "first %d reads (%d entries, %.3g of the workload's %d), %d warm-up + %d timed EM iterations (the call "
+                  "ends with the reference's final calculate_lnl) in %.1f s = %.1f ns/entry/iter, construction %.1f s; "
+                  "scaled linearly in entries to the full matrix; %s" % (
+                      rows, m.nnz, m.nnz / float(full_nnz), full_nnz, n_warm, n_iters, dt, dt / n_iters / m.nnz * 1e9,
+                      t_init, what),
         "host_cpus": os.cpu_count(),
-        "_lnl": float(em.lnl), "_rows": rows, "_pi": em.pi,
+        "_lnl": run.lnl, "_pi": run.pi, "_theta": run.theta, "_rows": rows,
     }
 
 
@@ -184,16 +237,27 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(nnz):
+def ncu_traffic(nnz, skew):
     """DRAM bytes per launch of the fused kernel from the committed ncu capture, scaled per entry (or None)."""
     p = os.path.join(ROOT, "profiles", "fused_kernel_traffic.json")
     if not os.path.exists(p):
         return None
     try:
         d = json.load(open(p))
-        return float(d["dram_bytes_per_entry"]) * nnz
+        key = "dram_bytes_per_entry_zipf" if skew and "dram_bytes_per_entry_zipf" in d else "dram_bytes_per_entry"
+        return float(d[key]) * nnz
     except Exception:
         return None
+
+
+def fused_kernel_name(layout):
+    if not layout["slices"]:
+        return "k_tiles<TILE_FUSED> (E-step + M-step accumulation, telescope_b200/csrc/tsc_tiles.cuh)"
+    s = "k_ell_fused (E-step + M-step accumulation over the clustered slice stream, telescope_b200/csrc/tsc_ell.cuh)"
+    if layout["residual_entries"]:
+        s += " + k_tiles<TILE_FUSED> on the residual CSR (%.3g of the ambiguous entries)" % (
+            layout["residual_entries"] / float(layout["residual_entries"] + layout["stream_entries"]))
+    return s
 
 
 # ----------------------------------------------------------------------------------------------- main arm
@@ -207,12 +271,17 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        r = run_cpu(a, W, K)
+        from telescope_b200.synthetic import synth_row_nnz
+        full_nnz = int(synth_row_nnz(a.reads, a.loci, a.avg, a.skew, SEED).sum())
+        rows = cpu_sample_rows(a, W + K, a.cpu_seconds)
+        r = run_cpu(a, W, K, rows, full_nnz)
+        n = max(1, a.gpus)
+        alg = full_nnz * 12.0 / n + (a.reads // n + 1) * 4.0
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": K,
             "warmup": W, "ms_per_step": 1e3 / r["value"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "n_reads": a.reads, "n_loci": a.loci},
+            "config": base_config(a, n, full_nnz, alg),
             "cpu_baseline": {k: v for k, v in r.items() if not k.startswith("_")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -223,12 +292,11 @@ def main():
     from telescope_b200 import _abi
     from telescope_b200.likelihood import TelescopeLikelihood
     from telescope_b200.synthetic import shard_bounds, synth_csr
+    from telescope_b200 import dist as tsc_dist
     import scipy.sparse as sp
 
-    # one process per GPU: the NCCL id travels through a file shared by the launcher's children; barriers and
-    # max-over-ranks go over the library's own communicator (no torch in the workers)
-    from telescope_b200 import dist as tsc_dist
-    dist = tsc_dist.rendezvous()
+    # one process per GPU: the ranks swap their exchange-buffer handles (or the NCCL id) through files shared by the
+    # launcher's children; barriers and max-over-ranks go over the library's own transport (no torch in the workers)
     live = {"tl": None}
 
     def _reduce(x, op):
@@ -245,46 +313,60 @@ def main():
     def sum_over_ranks(x):
         return _reduce(x, "sum")
 
+    def model(m, n_iter, max_score, **extra):
+        """A model over this rank's block `m`, joined with the other ranks' (fresh rendezvous per model)."""
+        kw = dict(devices=[local_rank], dist=tsc_dist.rendezvous(transport=a.transport), max_score=max_score,
+                  kernel=a.kernel, replicas=a.replicas, permute_columns=a.permute)
+        kw.update(extra)
+        return TelescopeLikelihood(m, Opts(n_iter), **kw)
+
+    def gen_block(skew, row_lo, row_hi, pinned):
+        ip, ix, raw = synth_csr(a.reads, a.loci, a.avg, skew, SEED, row_lo, row_hi)
+        keep = None
+        if pinned:
+            keep = (_abi.PinnedArray(ix.shape, np.int32), _abi.PinnedArray(raw.shape, np.uint16))
+            keep[0].array[:] = ix
+            keep[1].array[:] = raw
+            ix, raw = keep[0].array, keep[1].array
+        if ip[-1] < 2 ** 31:
+            ip = ip.astype(np.int32)      # scipy keeps int32 indices only next to an int32 indptr
+        return sp.csr_matrix((raw, ix, ip), shape=(row_hi - row_lo, a.loci), copy=False), keep
+
+    # the generator's score range is fixed (best hits reach 211 in any block of more than a few thousand reads), so
+    # the global maximum needs no exchange before the transport exists; it is re-checked after construction
+    GLOBAL_MAX = 211
+
     # ---- this rank's block of reads, generated straight into page-locked host memory
     lo, hi = shard_bounds(a.reads, world)[rank]
     t_gen = time.perf_counter()
-    ip, ix, raw = synth_csr(a.reads, a.loci, a.avg, a.skew, SEED, lo, hi)
-    pin_ix, pin_raw = _abi.PinnedArray(ix.shape, np.int32), _abi.PinnedArray(raw.shape, np.uint16)
-    pin_ix.array[:] = ix
-    pin_raw.array[:] = raw
-    del ix, raw
-    if ip[-1] < 2 ** 31:
-        ip = ip.astype(np.int32)      # scipy keeps int32 indices only next to an int32 indptr
-    m = sp.csr_matrix((pin_raw.array, pin_ix.array, ip), shape=(hi - lo, a.loci), copy=False)
+    m, pins = gen_block(a.skew, lo, hi, True)
     t_gen = time.perf_counter() - t_gen
     local_nnz = int(m.nnz)
-    # the generator's score range is fixed (best hits reach 211 in any block of more than a few thousand reads), so
-    # the global maximum needs no exchange before the communicator exists; it is re-checked after construction
-    max_score = 211 if world > 1 else int(pin_raw.array.max())
-
-    kw = dict(devices=[local_rank], dist=dist, max_score=max_score, kernel=a.kernel, replicas=a.replicas,
-              smem_table_cols=a.smem_table_cols, permute_columns=a.permute)
+    max_score = GLOBAL_MAX if world > 1 else int(m.data.max())
 
     # one-off library warm-up (CUDA module load, first allocations) on a toy matrix, as any long-lived caller has
     wi, wx, wr = synth_csr(4096, 64, 6, False, 1)
     warm = TelescopeLikelihood(sp.csr_matrix((wr, wx, wi), shape=(4096, 64)), Opts(2), devices=[local_rank])
     warm.em()
     warm.close()
-    # ---- e2e: the whole job through the public class, host buffers in, parameters out.  All ranks start together
-    # (no communicator exists yet, so the barrier goes through the launcher-shared temp files).
-    tsc_dist.file_barrier("e2e")
-    t0 = time.perf_counter()
-    tl = TelescopeLikelihood(m, Opts(K), **kw)
-    live["tl"] = tl
-    t_create = time.perf_counter() - t0
+
+    def timed_e2e(mat, tag):
+        """The whole job through the public class, host buffers in, parameters out.  All ranks start together."""
+        tsc_dist.file_barrier(tag)
+        t0 = time.perf_counter()
+        tl = model(mat, K, max_score)
+        live["tl"] = tl
+        t_create = time.perf_counter() - t0
+        tl.em()
+        _ = tl.pi.copy(), tl.theta.copy()
+        t = max_over_ranks(time.perf_counter() - t0)
+        return tl, t, t_create
+
+    tl, t_e2e, t_create = timed_e2e(m, "e2e")
     create_s, create_laps = tl.create_seconds, tl.create_laps
-    tl.em()
-    pi_e2e = tl.pi.copy()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    assert int(max_over_ranks(float(pin_raw.array.max()))) == max_score, "score range assumption violated"
+    assert int(max_over_ranks(float(m.data.max()))) == max_score, "score range assumption violated"
     total_nnz = int(sum_over_ranks(float(local_nnz)))
     c_e2e = tl.counters()
-    lnl_first = tl.lnl
 
     # ---- device-resident: W warm-up iterations, then exactly K timed ones.  Clocks are sampled from the warm-up to
     # the end of the extra kernel timings below (the GPU is under the same kind of load throughout).
@@ -304,41 +386,43 @@ def main():
     c1 = tl.counters()
     kms = tl.kernel_times_ms()
     kern_ms = max_over_ranks(float(np.mean(kms)) if len(kms) else float("nan"))
+    final_lnl = tl.lnl
 
     # other device passes of the path, timed alone (no host copies): standalone E-step (writes z), log-likelihood,
-    # one reassign mode
+    # one reassign mode; then the one-pass report through the public method (device pass + K-vectors to host)
     passes = {}
     for name in ("estep", "lnl", "reassign"):
         try:
             passes[name] = max_over_ranks(tl.time_pass(name, 3))
-        except Exception as exc:      # e.g. not enough memory for the 8 B/entry z buffer
+        except Exception:             # e.g. not enough memory for the 8 B/entry z buffer
             passes[name] = None
+    barrier()
+    t0 = time.perf_counter()
+    tl.report_colsums(0.9, "exclude")
+    t_report = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
+    layout = tl.layout_stats()
     value = K / (dev_ms * 1e-3)
     peak, peak_src = hbm_peak()
     rows_local = hi - lo
     alg_bytes = local_nnz * 12.0 + (rows_local + 1) * 4.0
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    traffic = ncu_traffic(local_nnz)
-    layout = tl.layout_stats()
-    fused_name = ("k_ell_fused (E-step + M-step accumulation over the clustered slice stream, telescope_b200/csrc/tsc_ell.cuh)"
-                  + (" + k_tiles<TILE_FUSED> on the residual CSR" if layout["residual_reads"] else "")
-                  if layout["slices"] else
-                  "k_tiles<TILE_FUSED> (E-step + M-step accumulation, telescope_b200/csrc/tsc_tiles.cuh)")
+    traffic = ncu_traffic(local_nnz, a.skew)
+    live["tl"] = None
+    tl.close()
 
     line = None
     if rank == 0:
+        cfg = base_config(a, world, total_nnz, alg_bytes)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": workload_name(a), "n_reads": a.reads, "n_loci": a.loci, "nnz": total_nnz,
-                "parallelism": "read-sharded x%d, 1 NCCL all-reduce of K doubles per iteration" % world if world > 1 else "1 GPU",
-                "l2": "per-iteration inputs (%.1f GB per GPU) are larger than L2, no flush needed" % (alg_bytes / 1e9),
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "notes": {
                 "timing": "CUDA events on the library stream around em(max_iter=K), max over ranks; includes the final "
                           "calculate_lnl pass like the reference's em()",
-                "kernel": a.kernel, "wall_ms_per_step": wall * 1e3 / K, "gen_s": round(t_gen, 2),
+                "kernel": a.kernel, "transport": a.transport if world > 1 else "none (1 GPU)",
+                "wall_ms_per_step": wall * 1e3 / K, "gen_s": round(t_gen, 2),
             },
             "clocks": clocks,
             "e2e": {
@@ -349,13 +433,21 @@ def main():
                         "(CUDA module load), nothing of the workload is cached" % (K, t_create),
                 "construction_s": t_create, "tsc_create_s": create_s, "tsc_create_laps_ms": create_laps,
             },
+            "e2e_report": {
+                "value": K / (t_e2e + t_report), "unit": UNIT, "report_s": t_report,
+                "what": "e2e plus Telescope.output_report's seven column sums in one device pass (model.py:432-458)",
+            },
             "gpu_launches": c1["launches"] - c0["launches"],
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": fused_name,
+                "traffic": traffic, "kernel": fused_kernel_name(layout),
                 "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "stream_bytes": layout["stream_bytes"],
+                "frac_dram": None if not traffic else traffic / (kern_ms * 1e-3) / 1e9 / peak,
+                "note": "achieved/frac use the ALGORITHMIC bytes of canonical CSR (12 B per entry, SURVEY 8d); the kernel "
+                        "itself moves `traffic` bytes (1-byte loci, unique reads skipped), frac_dram is on those",
             },
-            "final_lnl": tl.lnl,
+            "final_lnl": final_lnl,
             "layout": layout,
             "other_kernels": {
                 "estep_z": None if not passes.get("estep") else {
@@ -367,30 +459,109 @@ def main():
             },
         }
 
-    # ---- CPU arm beside it (rank 0, single-GPU run only) + parity of the GPU path on the same sample
-    if rank == 0 and world == 1 and not a.no_cpu:
+    if not a.no_extras:
+        # ---- e2e again from ordinary pageable arrays (what a scipy caller hands over)
+        mp_ = sp.csr_matrix((np.array(m.data), np.array(m.indices), np.array(m.indptr)), shape=m.shape, copy=False)
+        tl2, t_pg, t_pg_create = timed_e2e(mp_, "e2e_pageable")
+        if rank == 0:
+            line["e2e_pageable"] = {"value": K / t_pg, "unit": UNIT, "construction_s": t_pg_create,
+                                    "tsc_create_laps_ms": tl2.create_laps,
+                                    "what": "as e2e, but the CSR arrays are ordinary pageable numpy arrays"}
         live["tl"] = None
-        tl.close()
-        cb = run_cpu(a, 0, 2, csr=(ip, pin_ix.array, pin_raw.array))
-        rows = cb["_rows"]
-        sub = sp.csr_matrix((pin_raw.array[:ip[rows]], pin_ix.array[:ip[rows]], ip[:rows + 1]), shape=(rows, a.loci))
-        o2 = Opts(2)
-        g = TelescopeLikelihood(sub, o2, devices=[local_rank], kernel=a.kernel)
+        tl2.close()
+        del mp_
+
+    # ---- parity of the N-rank path against the CPU oracle on a sample of every rank's block
+    def parity(skew, rows_per_rank, iters, tag):
+        from oracle.em_numpy import EMOracle
+        tsc_dist.file_barrier("parity_" + tag)
+        bounds = shard_bounds(a.reads, world)
+        s_rows = [min(rows_per_rank, b[1] - b[0]) for b in bounds]
+        sub, _ = gen_block(skew, lo, lo + s_rows[rank], False)
+        g = model(sub, iters, GLOBAL_MAX)
         g.em()
-        line["parity"] = {
-            "sample_rows": rows, "iterations": 2,
+        counts = g.reassign_colsum("exclude")
+        out = None
+        if rank == 0:
+            parts = [synth_csr(a.reads, a.loci, a.avg, skew, SEED, b[0], b[0] + s) for b, s in zip(bounds, s_rows)]
+            offs = np.cumsum([0] + [int(p[0][-1]) for p in parts[:-1]])
+            ip = np.concatenate([np.zeros(1, dtype=np.int64)] + [p[0][1:] + off for p, off in zip(parts, offs)])
+            ix, raw = np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts])
+            assert int(raw.max()) == GLOBAL_MAX
+            o = EMOracle(ip, ix, raw, a.loci, -1.0, iters, 0, 200000).em()
+            nz = o.pi > 0
+            out = {
+                "sample_rows": int(sum(s_rows)), "sample_entries": int(ix.size), "ranks": world, "iterations": iters,
+                "lnl_rel_err": abs(g.lnl - o.lnl) / abs(o.lnl),
+                "pi_max_rel_err": float(np.max(np.abs(g.pi[nz] - o.pi[nz]) / o.pi[nz])),
+                "theta_max_rel_err": float(np.max(np.abs(g.theta - o.theta) / o.theta)),
+                "counts_bit_exact": bool(np.array_equal(counts, o.reassign_colsum("exclude"))),
+                "counts_total": int(counts.sum()), "tolerance": 1e-6,
+                "oracle": "oracle/em_numpy.py on the concatenated sample (rank 0), same seeded rows",
+            }
+        g.close()
+        return out
+
+    if not a.no_extras:
+        per_rank = cpu_sample_rows(a) if world == 1 else 250_000
+        p = parity(a.skew, per_rank, 3, "main")
+        if rank == 0:
+            line["parity"] = p
+
+    # ---- BASELINE.json config 5: Zipf reads-per-row (max 200), the divergence / long-read stress
+    if not a.no_extras and not a.skew:
+        del m, pins
+        mz, pz = gen_block(True, lo, hi, True)
+        tsc_dist.file_barrier("zipf")
+        tz = model(mz, 2, GLOBAL_MAX if world > 1 else int(mz.data.max()))
+        live["tl"] = tz
+        tz.em()
+        tz.max_iter = 8
+        barrier()
+        tz.em()
+        z_ms = max_over_ranks(tz.em_device_ms())
+        zk = tz.kernel_times_ms()
+        z_kern = max_over_ranks(float(np.mean(zk)))
+        z_nnz, z_rows = int(mz.nnz), hi - lo
+        z_total = int(sum_over_ranks(float(z_nnz)))
+        z_layout = tz.layout_stats()
+        z_lnl = tz.lnl
+        live["tl"] = None
+        tz.close()
+        del mz, pz
+        pzr = parity(True, 250_000, 2, "zipf")
+        if rank == 0:
+            zb = z_nnz * 12.0 + (z_rows + 1) * 4.0
+            line["other_configs"] = {"zipf": {
+                "workload": workload_name(a, True), "nnz": z_total, "steps": 8, "value": 8 / (z_ms * 1e-3), "unit": UNIT,
+                "ms_per_step": z_ms / 8, "fused_kernel_ms": z_kern, "algorithmic_bytes": zb,
+                "achieved_gbs": zb / (z_kern * 1e-3) / 1e9, "frac": zb / (z_kern * 1e-3) / 1e9 / peak,
+                "kernel": fused_kernel_name(z_layout), "layout": z_layout, "final_lnl": z_lnl, "parity": pzr,
+            }}
+
+    # ---- CPU arm beside it (rank 0, single-GPU run only): the reference on the same 4 % sample the parity used
+    if rank == 0 and world == 1 and not a.no_cpu:
+        rows = cpu_sample_rows(a)
+        cb = run_cpu(a, 0, 2, rows, total_nnz)
+        line["cpu_baseline"] = {k: v for k, v in cb.items() if not k.startswith("_")}
+        # and the GPU path against THAT run: same rows, same two iterations
+        sub, _ = gen_block(a.skew, 0, rows, False)
+        g = TelescopeLikelihood(sub, Opts(2), devices=[local_rank], kernel=a.kernel)
+        g.em()
+        nz = cb["_pi"] > 0
+        line["parity_vs_cpu_baseline"] = {
+            "kind": cb["kind"], "sample_rows": rows, "iterations": 2,
             "lnl_rel_err": abs(g.lnl - cb["_lnl"]) / abs(cb["_lnl"]),
-            "pi_max_rel_err": float(np.max(np.abs(g.pi - cb["_pi"]) / np.maximum(cb["_pi"], 1e-300))),
+            "pi_max_rel_err": float(np.max(np.abs(g.pi[nz] - cb["_pi"][nz]) / cb["_pi"][nz])),
+            "theta_max_rel_err": float(np.max(np.abs(g.theta - cb["_theta"]) / cb["_theta"])),
             "tolerance": 1e-6,
         }
         g.close()
-        line["cpu_baseline"] = {k: v for k, v in cb.items() if not k.startswith("_")}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        barrier()
+        tsc_dist.file_barrier("end")
         tsc_dist.cleanup()
-    tl.close()
     return 0
 
 

@@ -20,8 +20,9 @@
  *
  * Sharding: reads are split into contiguous row ranges, one shard per GPU, balanced by nnz.  One handle can drive
  * several GPUs of the box from one process (n_local_devices > 1), and/or be one of n_procs cooperating processes
- * (one per GPU under torchrun); either way the only data-path collective is one NCCL all-reduce of the K per-locus
- * M-step sums per EM iteration (plus a few one-off reductions at construction and after the loop).
+ * (one per GPU under torchrun); either way the only data-path exchange is the K per-locus M-step sums, once per EM
+ * iteration (plus a few one-off reductions at construction and after the loop) -- through peer-mapped memory inside
+ * the update kernel on one node (tsc_transport), or an NCCL all-reduce.
  */
 #ifndef TELESCOPE_B200_H
 #define TELESCOPE_B200_H
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TSC_ABI_VERSION 1
+#define TSC_ABI_VERSION 2
 
 typedef struct tsc_handle tsc_handle;
 
@@ -73,8 +74,20 @@ typedef struct {
     int32_t smem_acc_cols;     /* reserved (shared-memory fp64 atomics are CAS loops on sm_100a; not used) */
     int32_t permute_columns;   /* 1 = renumber loci by descending entry count internally, 0 = keep the caller's
                                   numbering (default: neighbouring loci share sectors, which the scatter-add likes) */
-    int32_t reserved[6];
+    int32_t transport;         /* tsc_transport: how the GPUs exchange the K per-locus sums of an iteration */
+    void* peer_buffer;         /* peer transport, n_procs > 1: this process's exchange buffer from
+                                  tsc_peer_buffer_create (the handle takes ownership) */
+    const void* peer_handles;  /* ... and the 64-byte CUDA IPC handles of all n_procs buffers, in rank order */
+    int32_t reserved[4];
 } tsc_config;
+
+/* exchange of the per-locus M-step sums between the GPUs of a model */
+typedef enum {
+    TSC_TRANSPORT_AUTO = 0,   /* peer when every GPU can map every other one's buffer, else NCCL */
+    TSC_TRANSPORT_PEER = 1,   /* one node: peer-mapped exchange buffers (peer access inside one process, CUDA IPC
+                                 between processes); the exchange is fused into the update kernel, no NCCL involved */
+    TSC_TRANSPORT_NCCL = 2    /* ncclAllReduce over a communicator built from nccl_id */
+} tsc_transport;
 
 /* library / environment */
 int tsc_abi_version(void);
@@ -83,6 +96,13 @@ int tsc_device_count(int32_t* n_out);
 /* path of libnccl.so.2 to dlopen (optional; default: $TELESCOPE_B200_NCCL, else the loader's search path) */
 int tsc_set_nccl_path(const char* path);
 int tsc_nccl_unique_id(void* out128);
+/* Peer transport with one process per GPU: allocate this rank's exchange buffer on `device` for a model with n_cols
+ * loci and `world` ranks, and export its 64-byte CUDA IPC handle.  The ranks swap the handles (any side channel; a
+ * file all-gather is in telescope_b200/dist.py) and pass buffer + all handles to tsc_create through tsc_config. */
+int tsc_peer_buffer_create(int32_t device, int32_t n_cols, int32_t world, void** buf_out, void* ipc_handle64_out);
+void tsc_peer_buffer_free(void* buf);     /* only for a buffer that never reached tsc_create */
+/* transport the handle ended up with (tsc_transport) */
+int tsc_get_transport(tsc_handle* h, int32_t* transport_out);
 void tsc_config_default(tsc_config* cfg);
 /* page-locked host memory for the CSR arrays (optional; uploads from it run at full PCIe speed) */
 void* tsc_pinned_alloc(uint64_t bytes);

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("TELESCOPE_B200_LIB") or os.path.join(_HERE, "libteles
 TSC_OK, TSC_ERR_ARG, TSC_ERR_CUDA, TSC_ERR_NCCL, TSC_ERR_STATE, TSC_ERR_ALLOC = range(6)
 METHODS = {"exclude": 0, "choose": 1, "average": 2, "conf": 3, "unique": 4, "all": 5}
 KERNELS = {"auto": 0, "rows": 1, "tiles": 2, "ell": 3}
+TRANSPORTS = {"auto": 0, "peer": 1, "nccl": 2}
 
 # every symbol the header declares; tests check the library exports exactly these
 SYMBOLS = (
@@ -22,7 +23,7 @@ SYMBOLS = (
     "tsc_config_default", "tsc_create", "tsc_destroy", "tsc_get_constants", "tsc_get_row_info", "tsc_get_q",
     "tsc_em", "tsc_get_kernel_times", "tsc_get_counters", "tsc_get_params", "tsc_set_params", "tsc_estep",
     "tsc_mstep", "tsc_calculate_lnl", "tsc_get_z", "tsc_reassign_nbest", "tsc_reassign_colsum",
-    "tsc_reassign_data", "tsc_get_em_device_ms", "tsc_pinned_alloc", "tsc_pinned_free", "tsc_time_pass", "tsc_allreduce_f64", "tsc_create_laps", "tsc_report", "tsc_choose_ties_colsum", "tsc_get_layout_stats",
+    "tsc_reassign_data", "tsc_get_em_device_ms", "tsc_pinned_alloc", "tsc_pinned_free", "tsc_time_pass", "tsc_allreduce_f64", "tsc_create_laps", "tsc_report", "tsc_choose_ties_colsum", "tsc_get_layout_stats", "tsc_peer_buffer_create", "tsc_peer_buffer_free", "tsc_get_transport",
 )
 
 
@@ -38,7 +39,10 @@ class TscConfig(C.Structure):
         ("smem_table_cols", C.c_int32),
         ("smem_acc_cols", C.c_int32),
         ("permute_columns", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("transport", C.c_int32),
+        ("peer_buffer", C.c_void_p),
+        ("peer_handles", C.c_void_p),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -92,6 +96,10 @@ def load():
     lib.tsc_create_laps.restype = C.c_char_p
     lib.tsc_allreduce_f64.argtypes = [vp, dp, i32, i32]
     lib.tsc_time_pass.argtypes = [vp, i32, i32, C.POINTER(C.c_float)]
+    lib.tsc_peer_buffer_create.argtypes = [i32, i32, i32, C.POINTER(vp), vp]
+    lib.tsc_peer_buffer_free.argtypes = [vp]
+    lib.tsc_peer_buffer_free.restype = None
+    lib.tsc_get_transport.argtypes = [vp, ip]
     lib.tsc_get_layout_stats.argtypes = [vp, C.POINTER(i64)]
     lib.tsc_get_counters.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.tsc_get_params.argtypes = [vp, dp, dp, dp, dp]

@@ -31,6 +31,7 @@
 #include "tsc_kernels.cuh"
 #include "tsc_tiles.cuh"
 #include "tsc_ell.cuh"
+#include "tsc_peer.cuh"
 
 using namespace tsc;
 
@@ -133,6 +134,15 @@ struct Shard {
     int grid_rows = 0, grid_tiles = 0;
     size_t smem_tiles = 0;
     int s_cols = 0;
+    // peer-memory transport (tsc_peer.cuh): this GPU's exchange buffer, every rank's buffer as mapped here
+    unsigned char* peer_own = nullptr;
+    std::vector<unsigned char*> peer_map;       // world entries; [world_rank] == peer_own
+    std::vector<char> peer_opened;              // mapped with cudaIpcOpenMemHandle (closed at destruction)
+    unsigned char** peer_ptrs_d = nullptr;
+    double* tail_partials = nullptr;
+    unsigned* tail_ticket = nullptr;
+    int* peer_err = nullptr;
+    void* xchg_ptr = nullptr;                   // argument slot of the generic all-reduce for temporaries
     // clustered sliced-ELL stream of the fused kernel (tsc_ell.cuh) + residual CSR for the reads it does not hold
     unsigned char* ell_stream = nullptr;
     long long ell_bytes = 0, ell_slices = 0, ell_reads = 0, ell_entries = 0;
@@ -150,6 +160,9 @@ struct tsc_handle {
     std::vector<Shard> shards;
     int K = 0, world = 1, n_procs = 1, proc_rank = 0;
     int R = 8, G = 8, kernel = TSC_KERNEL_TILES;
+    int transport = TSC_TRANSPORT_PEER;          // how the shards exchange K-vectors (TSC_TRANSPORT_*)
+    int kpad = 0, nb_tail = 1, cap = 0;         // exchange-buffer geometry (tsc_peer.cuh)
+    unsigned long long epoch_iter = 0, epoch_gen = 0;
     bool smem_tab = false;
     long long n_rows_user = 0, n_rows = 0, nnz = 0;
     std::vector<long long> rowmap;        // compacted read -> caller's read index (empty when no empty reads)
@@ -174,15 +187,39 @@ static inline int grid_for(long long work, int threads, int cap) {
     return (int)std::max<long long>(1, std::min<long long>(b, cap));
 }
 
+static PeerArgs peer_args(const tsc_handle* h, const Shard& s) {
+    return PeerArgs{s.peer_ptrs_d, h->world, s.world_rank, h->kpad, h->nb_tail, h->cap};
+}
+
+// In-place reduction of `count` 8-byte elements over every shard of every process.
 static int allreduce(tsc_handle* h, void* (*ptr_of)(Shard&), size_t count, ncclDataType_t dt, ncclRedOp_t op) {
     if (h->world == 1) return TSC_OK;
-    NC(g_nccl.GroupStart());
-    for (auto& s : h->shards) {
-        CU(cudaSetDevice(s.dev));
-        void* p = ptr_of(s);
-        NC(g_nccl.AllReduce(p, p, count, dt, op, s.comm, s.stream));
+    if (h->transport == TSC_TRANSPORT_NCCL) {
+        NC(g_nccl.GroupStart());
+        for (auto& s : h->shards) {
+            CU(cudaSetDevice(s.dev));
+            void* p = ptr_of(s);
+            NC(g_nccl.AllReduce(p, p, count, dt, op, s.comm, s.stream));
+        }
+        NC(g_nccl.GroupEnd());
+        return TSC_OK;
     }
-    NC(g_nccl.GroupEnd());
+    const int kind = (dt == ncclUint64) ? 2 : (op == ncclMax ? 1 : 0);
+    for (size_t done = 0; done < count;) {
+        const int n = (int)std::min<size_t>(count - done, (size_t)h->cap);
+        const unsigned long long epoch = ++h->epoch_gen;
+        for (auto& s : h->shards) {
+            CU(cudaSetDevice(s.dev));
+            unsigned long long* p = (unsigned long long*)ptr_of(s) + done;
+            const PeerArgs pa = peer_args(h, s);
+            if (kind == 0) k_peer_allreduce<0><<<1, 1024, 0, s.stream>>>(pa, p, n, epoch, s.peer_err);
+            else if (kind == 1) k_peer_allreduce<1><<<1, 1024, 0, s.stream>>>(pa, p, n, epoch, s.peer_err);
+            else k_peer_allreduce<2><<<1, 1024, 0, s.stream>>>(pa, p, n, epoch, s.peer_err);
+            LAUNCH(h);
+            CU(cudaGetLastError());
+        }
+        done += n;
+    }
     return TSC_OK;
 }
 #define ALLREDUCE(h, member_expr, count, dt, op)                                                   \
@@ -284,6 +321,7 @@ extern "C" void tsc_config_default(tsc_config* cfg) {
     cfg->smem_table_cols = -1;
     cfg->smem_acc_cols = -1;
     cfg->permute_columns = 0;
+    cfg->transport = TSC_TRANSPORT_AUTO;
 }
 
 static void free_shard(Shard& s) {
@@ -292,8 +330,12 @@ static void free_shard(Shard& s) {
     void* ptrs[] = {s.indptr, s.col, s.q, s.wy, s.tiles, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
                     s.pi_init, s.theta_init, s.pisum0, s.acc, s.thetasum, s.ones, s.tmp_a, s.tmp_b, s.tmp_c, s.colsum,
                     s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad,
-                    s.ell_stream, s.ell_index, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles};
+                    s.ell_stream, s.ell_index, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles,
+                    s.peer_ptrs_d, s.tail_partials, s.tail_ticket, s.peer_err};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (size_t r = 0; r < s.peer_map.size(); ++r)
+        if (r < s.peer_opened.size() && s.peer_opened[r] && s.peer_map[r]) cudaIpcCloseMemHandle(s.peer_map[r]);
+    if (s.peer_own) cudaFree(s.peer_own);
     if (s.st_host) cudaFreeHost(s.st_host);
     for (auto& e : s.ev_poll) if (e) cudaEventDestroy(e);
     for (auto& e : s.ev_k) if (e) cudaEventDestroy(e);
@@ -307,6 +349,133 @@ extern "C" void tsc_destroy(tsc_handle* h) {
     if (!h) return;
     for (auto& s : h->shards) free_shard(s);
     delete h;
+}
+
+
+// ------------------------------------------------------------------------------------------------- transport
+static void peer_geometry(int K, int* kpad, int* nb, int* cap) {
+    *kpad = (K + 31) & ~31;
+    *nb = (K + kTailBlockLoci - 1) / kTailBlockLoci;
+    *cap = 8 * *kpad + 64;
+}
+
+static int peer_buffer_alloc(int dev, int K, int world, unsigned char** out) {
+    int kpad, nb, cap;
+    peer_geometry(K, &kpad, &nb, &cap);
+    const size_t bytes = 8 * peer_buffer_words(world, kpad, nb, cap);
+    CU(cudaSetDevice(dev));
+    CU(cudaMalloc(out, bytes));
+    CU(cudaMemset(*out, 0, bytes));            // flags start at epoch 0, before anybody can map the buffer
+    CU(cudaDeviceSynchronize());
+    return TSC_OK;
+}
+
+extern "C" int tsc_peer_buffer_create(int32_t device, int32_t n_cols, int32_t world, void** buf_out, void* ipc_handle64_out) {
+    if (!buf_out || !ipc_handle64_out || n_cols <= 0 || world <= 0) return fail(TSC_ERR_ARG, "bad argument");
+    unsigned char* buf = nullptr;
+    int rc = peer_buffer_alloc(device, n_cols, world, &buf);
+    if (rc) return rc;
+    cudaIpcMemHandle_t hd;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaError_t e = cudaIpcGetMemHandle(&hd, buf);
+    if (e != cudaSuccess) { cudaFree(buf); return fail(TSC_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memcpy(ipc_handle64_out, &hd, 64);
+    *buf_out = buf;
+    return TSC_OK;
+}
+
+extern "C" void tsc_peer_buffer_free(void* buf) { if (buf) cudaFree(buf); }
+
+// Decide how the shards exchange K-vectors and set it up:
+//   peer  - every GPU maps every rank's exchange buffer (same process: peer access; one process per GPU: CUDA IPC
+//           handles passed in cfg.peer_handles).  Also used with a single GPU (its own buffer), so that the
+//           per-iteration tail is one kernel everywhere.
+//   nccl  - ncclCommInitRank + ncclAllReduce (several nodes' worth of generality; slower to set up).
+static int setup_transport(tsc_handle* h, const tsc_config& cfg) {
+    const int n_local = (int)h->shards.size();
+    peer_geometry(h->K, &h->kpad, &h->nb_tail, &h->cap);
+    int want = cfg.transport;
+    if (want != TSC_TRANSPORT_PEER && want != TSC_TRANSPORT_NCCL) {            // auto
+        want = TSC_TRANSPORT_PEER;
+        if (h->n_procs > 1 && !cfg.peer_handles) want = TSC_TRANSPORT_NCCL;
+        if (h->n_procs > 1 && n_local > 1) want = TSC_TRANSPORT_NCCL;
+        if (h->n_procs == 1 && n_local > 1) {
+            for (int i = 0; i < n_local && want == TSC_TRANSPORT_PEER; ++i)
+                for (int j = 0; j < n_local; ++j) {
+                    int can = 1;
+                    if (i != j) CU(cudaDeviceCanAccessPeer(&can, h->shards[i].dev, h->shards[j].dev));
+                    if (!can) { want = TSC_TRANSPORT_NCCL; break; }
+                }
+        }
+    }
+    h->transport = want;
+    if (want == TSC_TRANSPORT_NCCL) {
+        if (h->world == 1) { h->transport = TSC_TRANSPORT_PEER; want = TSC_TRANSPORT_PEER; }
+    }
+    if (want == TSC_TRANSPORT_NCCL) {
+        ncclUniqueId id;
+        int rc = nccl_load();
+        if (rc) return rc;
+        if (h->n_procs > 1) {
+            if (!cfg.nccl_id) return fail(TSC_ERR_ARG, "the NCCL transport over several processes needs nccl_id");
+            memcpy(&id, cfg.nccl_id, 128);
+        } else NC(g_nccl.GetUniqueId(&id));
+        NC(g_nccl.GroupStart());
+        for (auto& s : h->shards) {
+            CU(cudaSetDevice(s.dev));
+            NC(g_nccl.CommInitRank(&s.comm, h->world, id, s.world_rank));
+        }
+        NC(g_nccl.GroupEnd());
+    } else {
+        if (h->n_procs > 1 && n_local > 1) return fail(TSC_ERR_ARG, "the peer transport takes one GPU per process or one process");
+        if (h->n_procs > 1 && (!cfg.peer_buffer || !cfg.peer_handles))
+            return fail(TSC_ERR_ARG, "the peer transport over several processes needs peer_buffer and peer_handles");
+        for (auto& s : h->shards) {
+            s.peer_map.assign(h->world, nullptr);
+            s.peer_opened.assign(h->world, 0);
+            if (h->n_procs > 1) s.peer_own = (unsigned char*)cfg.peer_buffer;           // ownership moves to the handle
+            else { int rc = peer_buffer_alloc(s.dev, h->K, h->world, &s.peer_own); if (rc) return rc; }
+            s.peer_map[s.world_rank] = s.peer_own;
+        }
+        if (h->n_procs > 1) {
+            Shard& s = h->shards[0];
+            CU(cudaSetDevice(s.dev));
+            for (int r = 0; r < h->world; ++r) {
+                if (r == s.world_rank) continue;
+                cudaIpcMemHandle_t hd;
+                memcpy(&hd, (const char*)cfg.peer_handles + 64 * (size_t)r, 64);
+                void* p = nullptr;
+                cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess)
+                    return fail(TSC_ERR_CUDA, "cudaIpcOpenMemHandle(rank " + std::to_string(r) + "): " + cudaGetErrorString(e) +
+                                                  " -- the peer transport needs every GPU of the node visible to every rank");
+                s.peer_map[r] = (unsigned char*)p;
+                s.peer_opened[r] = 1;
+            }
+        } else if (n_local > 1) {
+            for (auto& a : h->shards) {
+                CU(cudaSetDevice(a.dev));
+                for (auto& b : h->shards) {
+                    if (&a == &b) continue;
+                    cudaError_t e = cudaDeviceEnablePeerAccess(b.dev, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+                    if (e != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                    a.peer_map[b.world_rank] = b.peer_own;
+                }
+            }
+        }
+        for (auto& s : h->shards) {
+            CU(cudaSetDevice(s.dev));
+            CU(cudaMalloc(&s.peer_ptrs_d, sizeof(unsigned char*) * h->world));
+            CU(cudaMemcpy(s.peer_ptrs_d, s.peer_map.data(), sizeof(unsigned char*) * h->world, cudaMemcpyHostToDevice));
+            CU(cudaMalloc(&s.tail_partials, sizeof(double) * h->nb_tail));
+            CU(cudaMalloc(&s.tail_ticket, sizeof(unsigned)));
+            CU(cudaMemset(s.tail_ticket, 0, sizeof(unsigned)));
+            CU(cudaMalloc(&s.peer_err, sizeof(int)));
+            CU(cudaMemset(s.peer_err, 0, sizeof(int)));
+        }
+    }
+    return TSC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------- create
@@ -569,7 +738,8 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, const CreateInput& 
     h->proc_rank = cfg.proc_rank;
     const int n_local = std::max(1, cfg.n_local_devices);
     h->world = h->n_procs * n_local;
-    if (h->n_procs > 1 && !cfg.nccl_id) return fail(TSC_ERR_ARG, "n_procs > 1 needs nccl_id");
+    if (h->n_procs > 1 && !cfg.nccl_id && !cfg.peer_handles)
+        return fail(TSC_ERR_ARG, "n_procs > 1 needs peer_handles (peer transport) or nccl_id (NCCL transport)");
     if (h->proc_rank < 0 || h->proc_rank >= h->n_procs) return fail(TSC_ERR_ARG, "proc_rank out of range");
 
     int ndev = 0;
@@ -631,15 +801,6 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         rb[i] = lo;
     }
 
-    // ---- NCCL
-    ncclUniqueId id;
-    if (h->world > 1) {
-        int rc = nccl_load();
-        if (rc) return rc;
-        if (h->n_procs > 1) memcpy(&id, cfg.nccl_id, 128);
-        else NC(g_nccl.GetUniqueId(&id));
-    }
-
     if (h->shards.empty()) h->shards.resize(n_local);
     for (int i = 0; i < n_local; ++i) {
         Shard& s = h->shards[i];
@@ -654,16 +815,12 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(cudaDeviceGetAttribute(&s.n_sm, cudaDevAttrMultiProcessorCount, s.dev));
     }
-    if (h->world > 1 && !h->shards[0].comm) {
-        NC(g_nccl.GroupStart());
-        for (auto& s : h->shards) {
-            CU(cudaSetDevice(s.dev));
-            NC(g_nccl.CommInitRank(&s.comm, h->world, id, s.world_rank));
-        }
-        NC(g_nccl.GroupEnd());
+    if (!h->shards[0].peer_own && !h->shards[0].comm) {
+        int rc = setup_transport(h, cfg);
+        if (rc) return rc;
     }
 
-    tm.lap("streams + nccl init");
+    tm.lap("streams + transport");
     // ---- tuning
     h->R = cfg.replicas > 0 ? std::min(cfg.replicas, 64) : 16;
     const double avg = n_rows ? (double)nnz / (double)n_rows : 1.0;
@@ -757,14 +914,8 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
     tm.lap("column signatures");
     {   // global per-locus entry counts -> internal numbering (descending count, ties by original index)
         static_assert(sizeof(unsigned long long) == 8, "");
-        if (h->world > 1) {
-            NC(g_nccl.GroupStart());
-            for (int i = 0; i < n_local; ++i) {
-                CU(cudaSetDevice(h->shards[i].dev));
-                NC(g_nccl.AllReduce(cnt_d[i], cnt_d[i], (size_t)K * 4, ncclUint64, ncclSum, h->shards[i].comm, h->shards[i].stream));
-            }
-            NC(g_nccl.GroupEnd());
-        }
+        for (int i = 0; i < n_local; ++i) h->shards[i].xchg_ptr = cnt_d[i];
+        ALLREDUCE(h, s.xchg_ptr, (size_t)K * 4, ncclUint64, ncclSum);
         for (auto& s : h->shards) {
             int bad = 0;
             CU(cudaSetDevice(s.dev));
@@ -1043,6 +1194,12 @@ extern "C" int tsc_get_layout_stats(tsc_handle* h, int64_t* out8) {
     return TSC_OK;
 }
 
+extern "C" int tsc_get_transport(tsc_handle* h, int32_t* transport_out) {
+    if (!h || !transport_out) return fail(TSC_ERR_ARG, "NULL argument");
+    *transport_out = h->transport;
+    return TSC_OK;
+}
+
 extern "C" int tsc_get_em_device_ms(tsc_handle* h, float* ms_out) {
     if (!h || !ms_out) return fail(TSC_ERR_ARG, "NULL argument");
     *ms_out = h->em_ms;
@@ -1249,18 +1406,33 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
             int rc = launch_fused(h, s, true);
             if (rc) return rc;
             if (&s == &s0) CU(cudaEventRecord(s0.ev_k[2 * it + 1], s.stream));
-            k_reduce_replicas<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.acc, K, h->R, s.thetasum, s.st);
-            LAUNCH(h);
-            CU(cudaGetLastError());
+            if (h->transport == TSC_TRANSPORT_NCCL) {
+                k_reduce_replicas<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.acc, K, h->R, s.thetasum, s.st);
+                LAUNCH(h);
+                CU(cudaGetLastError());
+            }
         }
-        ALLREDUCE(h, s.thetasum, (size_t)K, ncclFloat64, ncclSum);
-        for (auto& s : h->shards) {
-            CU(cudaSetDevice(s.dev));
-            UpdateArgs a{s.thetasum, s.pisum0, s.consts, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
-                         s.pi_init, s.theta_init, s.st, s.diffs, K, T, use_likelihood ? 1 : 0, eps, s.rep};
-            k_update<<<1, 1024, 0, s.stream>>>(a);
-            LAUNCH(h);
-            CU(cudaGetLastError());
+        if (h->transport == TSC_TRANSPORT_NCCL) {
+            ALLREDUCE(h, s.thetasum, (size_t)K, ncclFloat64, ncclSum);
+            for (auto& s : h->shards) {
+                CU(cudaSetDevice(s.dev));
+                UpdateArgs a{s.thetasum, s.pisum0, s.consts, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
+                             s.pi_init, s.theta_init, s.st, s.diffs, K, T, use_likelihood ? 1 : 0, eps, s.rep};
+                k_update<<<1, 1024, 0, s.stream>>>(a);
+                LAUNCH(h);
+                CU(cudaGetLastError());
+            }
+        } else {
+            // replica sum + exchange over peer memory + update + loop control: one kernel (tsc_peer.cuh)
+            for (auto& s : h->shards) {
+                CU(cudaSetDevice(s.dev));
+                TailArgs a{UpdateArgs{nullptr, s.pisum0, s.consts, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
+                                      s.pi_init, s.theta_init, s.st, s.diffs, K, T, use_likelihood ? 1 : 0, eps, s.rep},
+                           peer_args(h, s), s.acc, h->R, h->epoch_iter, s.tail_partials, s.tail_ticket};
+                k_tail<<<h->nb_tail, kTailThreads, 0, s.stream>>>(a);
+                LAUNCH(h);
+                CU(cudaGetLastError());
+            }
         }
         if (use_likelihood) {
             int rc = launch_lnl(h, nullptr, true, true,
@@ -1291,6 +1463,8 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
     EmState fin;
     CU(cudaSetDevice(s0.dev));
     CU(cudaMemcpy(&fin, s0.st, sizeof(EmState), cudaMemcpyDeviceToHost));
+    h->epoch_iter += (unsigned long long)T;      // the same on every rank, whatever each of them launched or skipped
+    if (fin.pad) return fail(TSC_ERR_STATE, "peer exchange timed out: another rank of this model stopped taking part");
     h->n_iter = fin.iter;
     h->converged = fin.converged;
     h->em_done = true;
@@ -1567,14 +1741,10 @@ extern "C" int tsc_report(tsc_handle* h, double thresh, int32_t final_method, in
         if (nbf_d) cudaFree(nbf_d);
         if (e != cudaSuccess) { free_all(); return fail(TSC_ERR_CUDA, std::string("report: ") + cudaGetErrorString(e)); }
     }
-    if (h->world > 1) {
-        ncclResult_t r = g_nccl.GroupStart();
-        for (size_t i = 0; i < h->shards.size() && r == ncclSuccess; ++i) {
-            cudaSetDevice(h->shards[i].dev);
-            r = g_nccl.AllReduce(out_d[i], out_d[i], (size_t)6 * K, ncclFloat64, ncclSum, h->shards[i].comm, h->shards[i].stream);
-        }
-        if (r == ncclSuccess) r = g_nccl.GroupEnd();
-        if (r != ncclSuccess) { free_all(); return fail(TSC_ERR_NCCL, std::string("report all-reduce: ") + g_nccl.GetErrorString(r)); }
+    for (size_t i = 0; i < h->shards.size(); ++i) h->shards[i].xchg_ptr = out_d[i];
+    {
+        const int rc_ar = allreduce(h, [](Shard& s) -> void* { return s.xchg_ptr; }, (size_t)6 * K, ncclFloat64, ncclSum);
+        if (rc_ar) { free_all(); return rc_ar; }
     }
     int rc = sync_all(h);
     Shard& s0 = h->shards[0];

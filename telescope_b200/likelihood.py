@@ -22,39 +22,49 @@ from .sparse_plus import draw_picks
 _INT_DTYPE = {"exclude": np.int8, "choose": np.int8, "unique": np.uint8, "all": np.uint8}
 
 
-def _nccl_env_defaults():
-    """The only collective on this path is a latency-bound all-reduce of K doubles, so communicator SETUP cost is
-    what matters: without NVLS (multicast) setup and with two channels ncclCommInitRank takes about half as long on
-    an 8 x B200 box and the per-iteration time is unchanged (profiles/r1_nccl_init.md).  Only variables the user has
-    not set are touched; TELESCOPE_B200_NCCL_TUNE=0 leaves NCCL alone."""
+def _nccl_env_tuning():
+    """Opt-in (TELESCOPE_B200_NCCL_TUNE=1) NCCL settings for the NCCL transport: the only collective on this path is a
+    latency-bound all-reduce of K doubles, so communicator SETUP cost is what matters -- without NVLS (multicast)
+    setup and with two channels ncclCommInitRank takes about half as long on an 8 x B200 box and the per-iteration
+    time is unchanged (profiles/r1_nccl_init.md).  The variables are process-global (every later communicator of the
+    process inherits them), which is why the library never sets them on its own."""
     import os
-    if os.environ.get("TELESCOPE_B200_NCCL_TUNE", "1") == "0":
+    if os.environ.get("TELESCOPE_B200_NCCL_TUNE", "0") != "1":
         return
     os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
     os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
 
 
 class DistInfo(object):
-    """How this process takes part in a multi-process run (one process per GPU, e.g. under torchrun)."""
+    """How this process takes part in a multi-process run (one process per GPU, e.g. under torchrun).
 
-    def __init__(self, n_procs=1, proc_rank=0, nccl_id=None):
-        self.n_procs, self.proc_rank, self.nccl_id = n_procs, proc_rank, nccl_id
+    transport "peer" (default on one node): the ranks' K-length sums travel through CUDA-IPC mapped peer memory inside
+    the update kernel; `allgather(tag, bytes) -> [bytes]` swaps the IPC handles at construction.  transport "nccl":
+    `nccl_id` is rank 0's 128-byte id."""
+
+    def __init__(self, n_procs=1, proc_rank=0, nccl_id=None, allgather=None, transport=None):
+        self.n_procs, self.proc_rank, self.nccl_id, self.allgather = n_procs, proc_rank, nccl_id, allgather
+        self.transport = transport or ("nccl" if nccl_id is not None else "peer")
 
 
 class TelescopeLikelihood(object):
 
     def __init__(self, score_matrix, opts, devices=None, dist=None, max_score=None, kernel="auto", replicas=0,
-                 smem_table_cols=-1, permute_columns=False):
+                 smem_table_cols=-1, permute_columns=False, transport="auto"):
         """score_matrix: csr_matrix (uint16) N reads x K loci; opts: em_epsilon, max_iter, pi_prior, theta_prior.
 
         devices: list of CUDA ordinals driven from this process (default [0]).  dist: DistInfo when this process
-        holds only its block of reads; `max_score` must then be the global maximum score.
+        holds only its block of reads; `max_score` must then be the global maximum score.  transport: "auto", "peer"
+        (exchange through peer-mapped GPU memory inside the update kernel; one node) or "nccl".
         """
         self._lib = _abi.load()
         self._h = None
         self.raw_scores = score_matrix
         if score_matrix.nnz >= 2 ** 31 and score_matrix.indptr.dtype != np.int64:
             raise ValueError("indptr must be int64 for >= 2^31 entries")
+        if dist is not None and dist.n_procs > 1 and max_score is None:
+            # every rank must build Q = expm1(100*s/max) with the SAME maximum (model.py:640 takes it over all reads)
+            raise ValueError("max_score (the global maximum score) is required when the reads are split over processes")
         self.max_score = score_matrix.max() if max_score is None else max_score        # model.py:640
         self.N, self.K = score_matrix.shape                                               # model.py:643
         self.scale_factor = 100.                                                          # model.py:652
@@ -98,13 +108,32 @@ class TelescopeLikelihood(object):
         self._dev_arr = (C.c_int32 * len(devices))(*devices)
         cfg.n_local_devices = len(devices)
         cfg.device_ids = C.cast(self._dev_arr, C.POINTER(C.c_int32))
-        self._nccl_id = None
+        self._nccl_id = self._peer_handles = None
+        cfg.transport = _abi.TRANSPORTS[transport]
         if dist is not None and dist.n_procs > 1:
             cfg.n_procs, cfg.proc_rank = dist.n_procs, dist.proc_rank
-            self._nccl_id = C.create_string_buffer(dist.nccl_id, 128)
-            cfg.nccl_id = C.cast(self._nccl_id, C.c_void_p)
-        if len(devices) > 1 or (dist is not None and dist.n_procs > 1):
-            _nccl_env_defaults()
+            if transport == "auto":
+                cfg.transport = _abi.TRANSPORTS[dist.transport]
+            if cfg.transport == _abi.TRANSPORTS["peer"]:
+                # every rank allocates its exchange buffer, the ranks swap the CUDA IPC handles (dist.allgather)
+                if len(devices) != 1 or dist.allgather is None:
+                    raise ValueError("the peer transport between processes takes one device per process and DistInfo.allgather")
+                buf, handle = C.c_void_p(), C.create_string_buffer(64)
+                _abi.check(self._lib.tsc_peer_buffer_create(devices[0], self.K, dist.n_procs, C.byref(buf), handle))
+                try:
+                    blobs = dist.allgather("ipc", handle.raw)
+                except Exception:
+                    self._lib.tsc_peer_buffer_free(buf)
+                    raise
+                self._peer_handles = C.create_string_buffer(b"".join(blobs), 64 * dist.n_procs)
+                cfg.peer_buffer, cfg.peer_handles = buf, C.cast(self._peer_handles, C.c_void_p)
+            else:
+                if dist.nccl_id is None:
+                    raise ValueError("the NCCL transport needs DistInfo.nccl_id (dist.rendezvous(transport='nccl'))")
+                self._nccl_id = C.create_string_buffer(dist.nccl_id, 128)
+                cfg.nccl_id = C.cast(self._nccl_id, C.c_void_p)
+        if cfg.transport != _abi.TRANSPORTS["peer"] and (len(devices) > 1 or (dist is not None and dist.n_procs > 1)):
+            _nccl_env_tuning()
             path = _abi.find_nccl()
             if path:
                 self._lib.tsc_set_nccl_path(path.encode())
@@ -294,6 +323,12 @@ class TelescopeLikelihood(object):
         ms = C.c_float(0)
         _abi.check(self._lib.tsc_time_pass(self._h, {"fused": 0, "estep": 1, "lnl": 2, "reassign": 3}[which], reps, C.byref(ms)))
         return ms.value
+
+    def transport(self):
+        """'peer' or 'nccl': how this model's GPUs exchange the per-locus sums."""
+        t = C.c_int32(0)
+        _abi.check(self._lib.tsc_get_transport(self._h, C.byref(t)))
+        return {v: k for k, v in _abi.TRANSPORTS.items()}[t.value]
 
     def layout_stats(self):
         """Device layout of local shard 0 (diagnostic): the clustered slice stream and the residual CSR."""

@@ -76,24 +76,58 @@ _RDZV_CHILD = """
 import sys, time
 sys.path.insert(0, %r)
 from telescope_b200 import dist
-d = dist.rendezvous(timeout=60)
+d = dist.rendezvous(timeout=60, transport="nccl")
 print("RDZV %%d %%d %%s" %% (d.proc_rank, d.n_procs, d.nccl_id.hex()))
-if d.proc_rank == 0:
-    time.sleep(1.0)
-    dist.cleanup()
+# a second rendezvous in the same launch must not see the first one's blobs
+blobs = dist.allgather("ipc", bytes([d.proc_rank]) * 64, timeout=60)
+again = dist.allgather("ipc", bytes([d.proc_rank + 10]) * 64, timeout=60)
+print("GATHER %%d %%s %%s" %% (d.proc_rank, "".join("%%d" %% b[0] for b in blobs), ",".join("%%d" %% b[0] for b in again)))
+dist.file_barrier("end")
+dist.cleanup()
 """
 
 
-def test_torch_free_rendezvous_hands_rank0s_nccl_id_to_every_rank():
-    """Two children of this process (as under torchrun, ranks share a parent) agree on one 128-byte NCCL id."""
+def _run_children(extra_env=None):
     import subprocess
     procs = []
     for r in (1, 0):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_PORT="29%03d" % (os.getpid() % 1000))
+        env.update(extra_env or {})
         procs.append(subprocess.Popen([sys.executable, "-c", _RDZV_CHILD % ROOT], env=env, stdout=subprocess.PIPE,
                                       universal_newlines=True, cwd=ROOT))
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+    return outs
+
+
+def test_torch_free_rendezvous_hands_rank0s_nccl_id_to_every_rank():
+    """Two children of this process (as under torchrun, ranks share a parent) agree on one 128-byte NCCL id, and the
+    blob all-gather (CUDA IPC handles in the peer transport) returns every rank's blob in rank order, call by call."""
+    outs = _run_children()
     got = sorted(l.split() for o in outs for l in o.splitlines() if l.startswith("RDZV"))
     assert [g[1] for g in got] == ["0", "1"] and got[0][2] == got[1][2] == "2"
     assert got[0][3] == got[1][3] and len(got[0][3]) == 256
+    gat = sorted(l.split() for o in outs for l in o.splitlines() if l.startswith("GATHER"))
+    assert [g[2] for g in gat] == ["01", "01"] and [g[3] for g in gat] == ["10,11", "10,11"]
+
+
+def test_rendezvous_key_is_unique_per_restart_attempt():
+    """A restarted worker group (TORCHELASTIC_RESTART_COUNT bumped) uses fresh files: ids never leak across attempts."""
+    a = _run_children({"TORCHELASTIC_RESTART_COUNT": "0", "TORCHELASTIC_RUN_ID": "t"})
+    b = _run_children({"TORCHELASTIC_RESTART_COUNT": "1", "TORCHELASTIC_RUN_ID": "t"})
+    ida = {l.split()[3] for o in a for l in o.splitlines() if l.startswith("RDZV")}
+    idb = {l.split()[3] for o in b for l in o.splitlines() if l.startswith("RDZV")}
+    assert len(ida) == 1 and len(idb) == 1 and ida != idb
+
+
+def test_multi_process_model_requires_the_global_max_score():
+    import pytest
+    import scipy.sparse as sp
+    sys.path.insert(0, ROOT)
+    from telescope_b200.likelihood import DistInfo, TelescopeLikelihood
+
+    class O(object):
+        em_epsilon, max_iter, pi_prior, theta_prior = 1e-7, 5, 0, 200000
+    m = sp.csr_matrix(np.array([[3, 5], [0, 7]], dtype=np.uint16))
+    with pytest.raises(ValueError, match="max_score"):
+        TelescopeLikelihood(m, O, dist=DistInfo(2, 0, b"\0" * 128))

@@ -6,6 +6,8 @@ pi, theta, posteriors z and the log-likelihood -- the only differences are summa
 (warp tree vs sequential) and in the per-locus M-step sums (atomics vs row order).  In practice they agree to
 ~1e-12, which the tests also assert where it is robust.
 """
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -214,18 +216,94 @@ def test_rows_and_tiles_kernels_agree_at_scale():
     a.close(); b.close(); c.close()
 
 
-def test_multi_gpu_in_process_matches_single():
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_multi_gpu_in_process_matches_oracle(transport):
+    """One process driving two GPUs (the CLI's --devices 0,1): every multi-shard branch -- shard boundaries, the
+    per-iteration exchange, grouped reductions, report/reassign offsets -- against the CPU oracle."""
     from telescope_b200 import _abi
     if _abi.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    m = _matrix(N=100000, K=3000, avg=20, skew=False, seed=51)
+    m = _matrix(N=100000, K=3000, avg=20, skew=True, seed=51)
     opts = Opts(max_iter=10)
-    a, b = _tl(m, opts), _tl(m, opts, devices=[0, 1])
-    a.em(); b.em()
-    assert a.n_iter == b.n_iter
+    a, b, o = _tl(m, opts), _tl(m, opts, devices=[0, 1], transport=transport), _oracle(m, opts)
+    assert b.transport() == transport
+    a.em(); b.em(); o.em()
+    assert a.n_iter == b.n_iter == o.n_iter
+    assert rel_err(b.pi, o.pi) < TIGHT and rel_err(b.theta, o.theta) < TIGHT and abs(b.lnl - o.lnl) <= TIGHT * abs(o.lnl)
     assert rel_err(a.pi, b.pi) < 1e-9 and abs(a.lnl - b.lnl) <= 1e-10 * abs(a.lnl)
-    assert np.array_equal(a.reassign_colsum("exclude"), b.reassign_colsum("exclude"))
+    assert rel_err(_dense_z(b.z, m), o.z) < RTOL
+    for method, initial in [("exclude", False), ("exclude", True), ("unique", False), ("all", True)]:
+        assert np.array_equal(b.reassign_colsum(method, 0.9, initial), o.reassign_colsum(method, 0.9, initial))
+    assert rel_err(b.reassign_colsum("conf"), o.reassign_colsum("conf")) < RTOL
+    rep = b.report_colsums(0.9, "exclude")
+    assert np.array_equal(rep["final"], o.reassign_colsum("exclude")) and np.array_equal(rep["init_best"], o.reassign_colsum("exclude", 0.9, True))
     a.close(); b.close()
+
+
+_RANK_CHILD = """
+import os, sys, json
+import numpy as np, scipy.sparse as sp
+sys.path.insert(0, %(root)r)
+from telescope_b200 import dist as tsc_dist
+from telescope_b200.likelihood import TelescopeLikelihood
+from telescope_b200.synthetic import shard_bounds, synth_csr
+rank, world, local = tsc_dist.env_world()
+N, K = %(N)d, %(K)d
+class O(object):
+    em_epsilon, max_iter, pi_prior, theta_prior = 1e-7, %(iters)d, 0, 200000
+lo, hi = shard_bounds(N, world)[rank]
+ip, ix, raw = synth_csr(N, K, 14, True, 77, lo, hi)
+m = sp.csr_matrix((raw, ix, ip), shape=(hi - lo, K))
+out = {}
+for rep in range(2):                      # twice: a second model in the same launch (fresh handles / ids)
+    tl = TelescopeLikelihood(m, O, devices=[local], dist=tsc_dist.rendezvous(transport=%(transport)r), max_score=211)
+    assert tl.transport() == %(transport)r
+    tl.em()
+    tl.em()                               # and a second loop on the same model (epochs keep growing)
+    counts = tl.reassign_colsum("exclude")
+    out = dict(pi=tl.pi.tolist(), theta=tl.theta.tolist(), lnl=tl.lnl, n_iter=tl.n_iter, counts=counts.tolist(),
+               gmax=float(tl.allreduce([float(raw.max())], "max")[0]))
+    tl.close()
+tsc_dist.file_barrier("end")
+tsc_dist.cleanup()
+print("RESULT " + json.dumps(out))
+"""
+
+
+@pytest.mark.parametrize("world,transport", [(2, "peer"), (2, "nccl"), (4, "peer"), (8, "peer")])
+def test_one_process_per_gpu_matches_oracle(world, transport):
+    """BASELINE.json config 3's question: `world` ranks as under torchrun (one process per GPU, RANK/WORLD_SIZE in the
+    environment) against the single-process CPU oracle on the whole matrix -- pi, theta, lnl to 1e-9, `exclude`
+    counts bit-exact, and every rank ends with bit-identical parameters."""
+    import json
+    import subprocess
+    import sys
+    from telescope_b200 import _abi
+    from telescope_b200.synthetic import synth_csr
+    if _abi.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    N, K, iters = 120000, 2500, 6
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _RANK_CHILD % dict(root=root, N=N, K=K, iters=iters, transport=transport)
+    port = "29%03d" % (os.getpid() % 1000)
+    procs = [subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, universal_newlines=True, cwd=root,
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_PORT=port))
+             for r in range(world)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    res = [json.loads([l for l in o.splitlines() if l.startswith("RESULT ")][-1][7:]) for o in outs]
+    ip, ix, raw = synth_csr(N, K, 14, True, 77)
+    o = EMOracle(ip, ix, raw, K, 1e-7, iters, 0, 200000).em()
+    o.max_iter = iters
+    o.em()                                   # the children ran em() twice, continuing from their parameters
+    for r in res:
+        assert r["pi"] == res[0]["pi"] and r["theta"] == res[0]["theta"] and r["lnl"] == res[0]["lnl"]
+        assert r["gmax"] == 211.0
+    g = res[0]
+    assert g["n_iter"] == o.n_iter
+    assert rel_err(g["pi"], o.pi) < TIGHT and rel_err(g["theta"], o.theta) < TIGHT
+    assert abs(g["lnl"] - o.lnl) <= TIGHT * abs(o.lnl)
+    assert np.array_equal(np.array(g["counts"]), o.reassign_colsum("exclude"))
 
 
 def test_large_matrix_with_empty_reads_takes_the_compaction_path():

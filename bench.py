@@ -69,7 +69,7 @@ def parse_args():
     ap.add_argument("--skew", action="store_true", help="config 5 as the main workload: Zipf reads-per-row (max 200)")
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--replicas", type=int, default=0)
-    ap.add_argument("--transport", default="nccl", choices=["peer", "nccl"])
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--cpu-seconds", type=float, default=170.0, help="--impl reference: CPU budget for W+K iterations")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip pageable e2e, parity and the Zipf configuration")

@@ -533,16 +533,36 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
 
 // Flat tiles of whole reads (tsc_tiles.cuh) over a device-resident read-pointer array: count per chunk, prefix on the
 // host (a few thousand chunks), fill.
+struct Arena {               // bump allocator over device memory that is already there (dead upload buffers)
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    void* take(size_t bytes) {
+        const size_t a = (off + 255) & ~(size_t)255;
+        if (!base || a + bytes > cap) return nullptr;
+        off = a + bytes;
+        return base + a;
+    }
+};
+
 struct DevBuf {              // device temporaries released on every exit path
     std::vector<void*> p;
+    Arena* arena = nullptr;  // tried first; cudaMalloc only when it is full (every cudaMalloc/cudaFree of a large
+                             // block costs milliseconds and a device synchronisation)
     ~DevBuf() { for (void* q : p) if (q) cudaFree(q); }
     template <typename T> cudaError_t alloc(T** out, size_t n) {
+        const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+        if (arena) { void* q = arena->take(bytes); if (q) { *out = (T*)q; return cudaSuccess; } }
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+        cudaError_t e = cudaMalloc(&q, bytes);
         *out = (T*)q;
         if (e == cudaSuccess) p.push_back(q);
         return e;
     }
+    void keep(void* q) {     // q outlives the buffer: true when it was cudaMalloc'ed here (the caller now owns it)
+        auto it = std::find(p.begin(), p.end(), q);
+        if (it != p.end()) p.erase(it);
+    }
+    bool owns(void* q) const { return std::find(p.begin(), p.end(), q) != p.end(); }
 };
 
 static int build_tiles(tsc_handle* h, Shard& s, const long long* indptr_d, long long n_rows, Tile** tiles_out,
@@ -584,9 +604,11 @@ static int build_tiles(tsc_handle* h, Shard& s, const long long* indptr_d, long 
 
 // out[0..n] = exclusive prefix sums of in[0..n) on the shard's stream (tsc_ell.cuh scan kernels)
 template <typename T>
-static int device_scan(tsc_handle* h, Shard& s, const T* in, long long n, long long* out) {
+static int device_scan(tsc_handle* h, Shard& s, const T* in, long long n, long long* out, Arena* arena = nullptr) {
     const int nb = (int)std::max<long long>(1, (n + kScanItems - 1) / kScanItems);
     DevBuf tmp;
+    Arena mark;
+    if (arena) { mark = *arena; tmp.arena = arena; }
     long long* tot = nullptr;
     CU(tmp.alloc(&tot, (size_t)nb + 1));
     k_scan_local<T><<<nb, 1024, 0, s.stream>>>(in, n, out, tot);
@@ -595,6 +617,7 @@ static int device_scan(tsc_handle* h, Shard& s, const T* in, long long n, long l
     h->launches += 3;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s.stream));      // tot is released on return
+    if (arena) arena->off = mark.off;
     return TSC_OK;
 }
 
@@ -605,13 +628,19 @@ static int fetch_ll(Shard& s, const long long* dev, long long* host) {
 }
 
 // The clustered sliced-ELL stream of the fused kernel and the residual CSR (tsc_ell.cuh), from the shard's finished
-// q / col / indptr / wy arrays.  One-off; every array it allocates belongs to the shard.
-static int build_ell(tsc_handle* h, Shard& s) {
+// q / col / indptr / wy arrays.  One-off; what it keeps belongs to the shard.  `arena`: dead device memory (the raw
+// upload buffers) that serves the temporaries.
+static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
+    auto lap = [&](const char* what) { if (tm.on) cudaStreamSynchronize(s.stream); tm.lap(what); };
     const int K = h->K;
     const long long n_rows = s.n_rows;
     CU(cudaSetDevice(s.dev));
     DevBuf tmp;
+    tmp.arena = arena;
     int* key = nullptr;
+    unsigned long long* counters = nullptr;       // [0] ambiguous reads, [1] their entries, [2] residual cursor
+    CU(tmp.alloc(&counters, 4));
+    CU(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 4, s.stream));
     const bool ell_ok = n_rows > 0 && (long long)K * (1 << kEllLenBits) < (1LL << 31);
     long long n_cand = 0;
     int* sorted = nullptr;
@@ -629,9 +658,10 @@ static int build_ell(tsc_handle* h, Shard& s) {
         k_ell_classify<<<g, 256, 0, s.stream>>>(s.indptr, n_rows, s.col, n_keys, key, hist);
         LAUNCH(h);
         CU(cudaGetLastError());
-        int rc = device_scan<unsigned>(h, s, hist, n_keys, bin_start);
+        int rc = device_scan<unsigned>(h, s, hist, n_keys, bin_start, arena);
         if (rc) return rc;
         if ((rc = fetch_ll(s, bin_start + n_keys, &n_cand))) return rc;
+        lap("  ell classify+hist+scan");
         if (n_cand > 0) {
             CU(tmp.alloc(&sorted, n_cand));
             k_ell_scatter<<<g, 256, 0, s.stream>>>(key, n_rows, bin_start, cursor, sorted);
@@ -641,16 +671,17 @@ static int build_ell(tsc_handle* h, Shard& s) {
     }
     if (n_cand > 0) {
         const long long n_slices = (n_cand + kEllReads - 1) / kEllReads;
-        int4* hdr = nullptr;
         int* rec_bytes = nullptr;
         long long* rec_off = nullptr;
-        CU(tmp.alloc(&hdr, n_slices));
+        CU(cudaMalloc(&s.ell_index, sizeof(int4) * n_slices));      // kept: the kernel's record index
         CU(tmp.alloc(&rec_bytes, n_slices));
         CU(tmp.alloc(&rec_off, (size_t)n_slices + 1));
-        k_ell_slices<<<grid_for(n_slices, 128, s.n_sm * 16), 128, 0, s.stream>>>(s.indptr, s.col, sorted, n_cand, n_slices, key, hdr, rec_bytes);
+        lap("  ell scatter");
+        k_ell_slices<<<grid_for(n_slices, 128, s.n_sm * 16), 128, 0, s.stream>>>(s.indptr, s.col, sorted, n_cand, n_slices, key,
+                                                                                s.ell_index, rec_bytes);
         LAUNCH(h);
         CU(cudaGetLastError());
-        int rc = device_scan<int>(h, s, rec_bytes, n_slices, rec_off);
+        int rc = device_scan<int>(h, s, rec_bytes, n_slices, rec_off, arena);
         if (rc) return rc;
         long long total = 0;
         if ((rc = fetch_ll(s, rec_off + n_slices, &total))) return rc;
@@ -658,37 +689,37 @@ static int build_ell(tsc_handle* h, Shard& s) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ell_fused, 32, kEllSmem));
         const int warps = s.n_sm * std::max(per_sm, 1);
         const long long n_seg = (n_slices + 31) / 32;      // a warp's unit of work between two window flushes
+        lap("  ell slices+scan");
         if (total >= (1LL << 36)) return fail(TSC_ERR_ARG, "slice stream of one GPU exceeds 64 GB");
         CU(cudaMalloc(&s.ell_stream, (size_t)total));
+        lap("  ell stream malloc");
         k_ell_fill<<<grid_for(n_slices * 32, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, s.col, s.q, s.wy, sorted, n_cand, n_slices,
-                                                                                   hdr, rec_off, s.ell_stream);
+                                                                                   s.ell_index, rec_off, s.ell_stream);
         LAUNCH(h);
         CU(cudaGetLastError());
-        s.ell_index = hdr;                     // kept: the kernel's record index
-        tmp.p.erase(std::find(tmp.p.begin(), tmp.p.end(), (void*)hdr));
-        CU(cudaStreamSynchronize(s.stream));
         s.ell_bytes = total;
         s.ell_slices = n_slices;
         s.ell_grid = (int)std::min<long long>(n_seg, warps);
+        lap("  ell fill");
     }
     // ---- residual CSR: ambiguous reads without a slot in the stream (key < 0, or every ambiguous read when the
-    // stream could not be built)
+    // stream could not be built).  Usually a handful: they are counted first and then appended in whatever order the
+    // atomics give -- the order of the residual's reads is irrelevant, only each read's entries stay together.
     {
-        int *flag = nullptr, *rlen = nullptr;
-        long long *row_pos = nullptr, *ent_pos = nullptr;
-        CU(tmp.alloc(&flag, n_rows));
-        CU(tmp.alloc(&rlen, n_rows));
-        CU(tmp.alloc(&row_pos, (size_t)n_rows + 1));
-        CU(tmp.alloc(&ent_pos, (size_t)n_rows + 1));
         const int g = grid_for(n_rows, 256, s.n_sm * 16);
-        k_res_flags<<<g, 256, 0, s.stream>>>(s.indptr, n_rows, key, flag, rlen);
+        k_res_count<<<g, 256, 0, s.stream>>>(s.indptr, n_rows, key, counters);
         LAUNCH(h);
         CU(cudaGetLastError());
-        int rc = device_scan<int>(h, s, flag, n_rows, row_pos);
-        if (!rc) rc = device_scan<int>(h, s, rlen, n_rows, ent_pos);
-        if (!rc) rc = fetch_ll(s, row_pos + n_rows, &s.res_rows);
-        if (!rc) rc = fetch_ll(s, ent_pos + n_rows, &s.res_nnz);
-        if (rc) return rc;
+        unsigned long long cnt[4];
+        CU(cudaMemcpyAsync(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        const long long amb_rows = (long long)cnt[0], amb_nnz = (long long)cnt[1];
+        s.res_rows = (long long)(cnt[2] >> kResShift);
+        s.res_nnz = (long long)(cnt[2] & ((1ULL << kResShift) - 1ULL));
+        s.ell_reads = amb_rows - s.res_rows;
+        s.ell_entries = amb_nnz - s.res_nnz;
+        lap("  residual count");
+        if (s.res_rows >= (1LL << (64 - kResShift))) return fail(TSC_ERR_ARG, "too many reads outside the slice stream on one GPU");
         if (s.res_rows > 0) {
             const size_t pad = 256;
             CU(cudaMalloc(&s.res_indptr, sizeof(long long) * (s.res_rows + 1)));
@@ -697,33 +728,17 @@ static int build_ell(tsc_handle* h, Shard& s) {
             CU(cudaMalloc(&s.res_wy, sizeof(double) * s.res_rows));
             CU(cudaMemsetAsync(s.res_col + s.res_nnz, 0, sizeof(int) * pad, s.stream));
             CU(cudaMemsetAsync(s.res_q + s.res_nnz, 0, sizeof(double) * pad, s.stream));
-            k_res_copy<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, flag, row_pos, ent_pos,
-                                                                                   s.res_indptr, s.res_col, s.res_q, s.res_wy);
+            CU(cudaMemsetAsync(counters + 3, 0, sizeof(unsigned long long), s.stream));
+            k_res_append<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, key, counters + 3,
+                                                                                     s.res_indptr, s.res_col, s.res_q, s.res_wy);
             LAUNCH(h);
             CU(cudaMemcpyAsync(s.res_indptr + s.res_rows, &s.res_nnz, sizeof(long long), cudaMemcpyHostToDevice, s.stream));
             CU(cudaGetLastError());
             CU(cudaStreamSynchronize(s.stream));
-            rc = build_tiles(h, s, s.res_indptr, s.res_rows, &s.res_tiles, &s.res_n_tiles, &s.res_n_long);
+            int rc = build_tiles(h, s, s.res_indptr, s.res_rows, &s.res_tiles, &s.res_n_tiles, &s.res_n_long);
             if (rc) return rc;
+            lap("  residual copy+tiles");
         }
-    }
-    {   // reads / entries that made it into the stream = ambiguous - residual
-        DevBuf t2;
-        int *flag = nullptr, *rlen = nullptr;
-        long long* pos = nullptr;
-        CU(t2.alloc(&flag, n_rows));
-        CU(t2.alloc(&rlen, n_rows));
-        CU(t2.alloc(&pos, (size_t)n_rows + 1));
-        k_res_flags<<<grid_for(n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, nullptr, flag, rlen);
-        LAUNCH(h);
-        long long amb_rows = 0, amb_nnz = 0;
-        int rc = device_scan<int>(h, s, flag, n_rows, pos);
-        if (!rc) rc = fetch_ll(s, pos + n_rows, &amb_rows);
-        if (!rc) rc = device_scan<int>(h, s, rlen, n_rows, pos);
-        if (!rc) rc = fetch_ll(s, pos + n_rows, &amb_nnz);
-        if (rc) return rc;
-        s.ell_reads = amb_rows - s.res_rows;
-        s.ell_entries = amb_nnz - s.res_nnz;
     }
     CU(cudaStreamSynchronize(s.stream));
     return TSC_OK;
@@ -1013,7 +1028,13 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         for (auto& s : h->shards) {
             CU(cudaSetDevice(s.dev));
             CU(cudaFuncSetAttribute(k_ell_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEllSmem));
-            int rc = build_ell(h, s);
+            Arena arena;
+            {   // the raw uploads are dead once Q is built: their memory serves the temporaries of the clustering
+                const int i = (int)(&s - &h->shards[0]);
+                CU(cudaStreamSynchronize(s.stream));
+                if (colin_d[i] && s.nnz > 0) { arena.base = (char*)colin_d[i]; arena.cap = sizeof(int) * (size_t)s.nnz; }
+            }
+            int rc = build_ell(h, s, tm, &arena);
             if (rc) return rc;
         }
         tm.lap("clustered ELL stream");

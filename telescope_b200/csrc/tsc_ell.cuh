@@ -229,31 +229,56 @@ __global__ void __launch_bounds__(256) k_ell_fill(const long long* __restrict__ 
     }
 }
 
-// Residual CSR = ambiguous reads that are not in the stream.  flag/len per read, then (after the scans) the copy.
-__global__ void k_res_flags(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ key,
-                            int* __restrict__ flag, int* __restrict__ rlen) {
+// Residual CSR = ambiguous reads that are not in the stream (key < 0; key == nullptr: every ambiguous read).
+// counters[0] += ambiguous reads, [1] += their entries, [2] += (1 << kResShift | entries) per residual read.
+constexpr int kResShift = 38;     // a cursor packs (reads << 38 | entries): < 2^26 reads and < 2^38 entries per GPU
+
+__global__ void k_res_count(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ key,
+                            unsigned long long* __restrict__ counters) {
+    unsigned long long rows = 0, ents = 0, res = 0;
     long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; r < n_rows; r += stride) {
         const long long len = ip[r + 1] - ip[r];
-        const bool res = (len >= 2) && (key == nullptr || key[r] < 0);
-        flag[r] = res ? 1 : 0;
-        rlen[r] = res ? (int)min(len, (long long)0x7fffffff) : 0;
+        if (len < 2) continue;
+        ++rows;
+        ents += (unsigned long long)len;
+        if (key == nullptr || key[r] < 0) res += (1ULL << kResShift) | (unsigned long long)len;
+    }
+    // warp totals first: three atomics per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        rows += __shfl_xor_sync(0xffffffffu, rows, o);
+        ents += __shfl_xor_sync(0xffffffffu, ents, o);
+        res += __shfl_xor_sync(0xffffffffu, res, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (rows) atomicAdd(counters + 0, rows);
+        if (ents) atomicAdd(counters + 1, ents);
+        if (res) atomicAdd(counters + 2, res);
     }
 }
 
-__global__ void __launch_bounds__(256) k_res_copy(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ col,
-                                                  const double* __restrict__ q, const double* __restrict__ wy,
-                                                  const int* __restrict__ flag, const long long* __restrict__ row_pos,
-                                                  const long long* __restrict__ ent_pos, long long* __restrict__ ip_out,
-                                                  int* __restrict__ col_out, double* __restrict__ q_out,
-                                                  double* __restrict__ wy_out) {
+// 8 lanes per read; a residual read takes its place (read slot, first entry) from one packed atomic, so the read
+// pointers come out increasing in slot order whatever order the reads arrive in.
+__global__ void __launch_bounds__(256) k_res_append(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ col,
+                                                    const double* __restrict__ q, const double* __restrict__ wy,
+                                                    const int* __restrict__ key, unsigned long long* __restrict__ cursor,
+                                                    long long* __restrict__ ip_out, int* __restrict__ col_out,
+                                                    double* __restrict__ q_out, double* __restrict__ wy_out) {
     const int lane = threadIdx.x & 7;
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
     long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
     const long long stride = ((long long)gridDim.x * blockDim.x) >> 3;
-    for (; r < n_rows; r += stride) {
-        if (!flag[r]) continue;
-        const long long b = ip[r], e = ip[r + 1], o = ent_pos[r], rp = row_pos[r];
+    const long long r_end = ((n_rows + stride - 1) / stride) * stride;       // every group runs the same trip count
+    for (; r < r_end; r += stride) {
+        long long b = 0, e = 0;
+        bool res = false;
+        if (r < n_rows) { b = ip[r]; e = ip[r + 1]; res = (e - b >= 2) && (key == nullptr || key[r] < 0); }
+        unsigned long long old = 0;
+        if (res && lane == 0) old = atomicAdd(cursor, (1ULL << kResShift) | (unsigned long long)(e - b));
+        old = __shfl_sync(gmask, old, (threadIdx.x & 31) & ~7);
+        if (!res) continue;
+        const long long rp = (long long)(old >> kResShift), o = (long long)(old & ((1ULL << kResShift) - 1ULL));
         if (lane == 0) { ip_out[rp] = o; wy_out[rp] = wy[r]; }
         for (long long k = b + lane; k < e; k += 8) { col_out[o + (k - b)] = col[k]; q_out[o + (k - b)] = q[k]; }
     }

@@ -143,6 +143,7 @@ struct Shard {
     unsigned* tail_ticket = nullptr;
     int* peer_err = nullptr;
     void* xchg_ptr = nullptr;                   // argument slot of the generic all-reduce for temporaries
+    LogTab* log_tab = nullptr;                  // table of log1p_big (tsc_kernels.cuh)
     // clustered sliced-ELL stream of the fused kernel (tsc_ell.cuh) + residual CSR for the reads it does not hold
     unsigned char* ell_stream = nullptr;
     long long ell_bytes = 0, ell_slices = 0, ell_reads = 0, ell_entries = 0;
@@ -331,7 +332,7 @@ static void free_shard(Shard& s) {
                     s.pi_init, s.theta_init, s.pisum0, s.acc, s.thetasum, s.ones, s.tmp_a, s.tmp_b, s.tmp_c, s.colsum,
                     s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad,
                     s.ell_stream, s.ell_index, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles,
-                    s.peer_ptrs_d, s.tail_partials, s.tail_ticket, s.peer_err};
+                    s.peer_ptrs_d, s.tail_partials, s.tail_ticket, s.peer_err, s.log_tab};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (size_t r = 0; r < s.peer_map.size(); ++r)
         if (r < s.peer_opened.size() && s.peer_opened[r] && s.peer_map[r]) cudaIpcCloseMemHandle(s.peer_map[r]);
@@ -1009,6 +1010,9 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         s.grid_rows = s.n_sm * 4;                   // 512-thread blocks, persistent grid-stride
         s.grid_tiles = s.n_sm * 2;                  // refined below from the occupancy of the tile kernel
         CU(cudaMalloc(&s.partials, sizeof(double) * (s.n_sm * 32)));
+        CU(cudaMalloc(&s.log_tab, sizeof(LogTab) * kLogTab));
+        k_log_table<<<1, kLogTab, 0, s.stream>>>(s.log_tab);
+        LAUNCH(h);
         k_row_init<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(csr_of(s), s.wy, s.scalars, s.pisum0);
         LAUNCH(h);
         CU(cudaGetLastError());
@@ -1284,7 +1288,7 @@ extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float
                 launch_tiles<TILE_Z>(s, a, false);
                 break;
             case 2:
-                a.tab_amb = ta; a.tab_uni = tu; a.inner_amb = s.pt; a.inner_uni = s.pi; a.partials = s.partials;
+                a.tab_amb = ta; a.tab_uni = tu; a.inner_amb = s.pt; a.inner_uni = s.pi; a.partials = s.partials; a.log_tab = s.log_tab;
                 launch_tiles<TILE_LNL>(s, a, false);
                 break;
             case 3: {
@@ -1366,7 +1370,7 @@ static int launch_lnl(tsc_handle* h, const double* (*zin_of)(Shard&), bool from_
             TileArgs a{};
             a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col;
             a.tab_amb = s.pt_prev; a.tab_uni = s.pi_prev; a.inner_amb = ia(s); a.inner_uni = iu(s);
-            a.K = h->K; a.st = st; a.partials = s.partials;
+            a.K = h->K; a.st = st; a.partials = s.partials; a.log_tab = s.log_tab;
             nparts = s.grid_tiles;
             launch_tiles<TILE_LNL>(s, a, false);
         } else {
@@ -1410,7 +1414,10 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
     }
     Shard& s0 = h->shards[0];
     CU(cudaSetDevice(s0.dev));
-    while ((int)s0.ev_k.size() < 2 * T) {
+    // kernel-time events: a bounded pool (the first kTimedIters iterations of a call are timed), created on demand
+    constexpr int kTimedIters = 512;
+    const int n_timed = std::min(T, kTimedIters);
+    while ((int)s0.ev_k.size() < 2 * n_timed) {
         cudaEvent_t e;
         CU(cudaEventCreate(&e));
         s0.ev_k.push_back(e);
@@ -1423,10 +1430,10 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
     for (int it = 0; it < T && !stop; ++it) {
         for (auto& s : h->shards) {
             CU(cudaSetDevice(s.dev));
-            if (&s == &s0) CU(cudaEventRecord(s0.ev_k[2 * it], s.stream));
+            if (&s == &s0 && it < n_timed) CU(cudaEventRecord(s0.ev_k[2 * it], s.stream));
             int rc = launch_fused(h, s, true);
             if (rc) return rc;
-            if (&s == &s0) CU(cudaEventRecord(s0.ev_k[2 * it + 1], s.stream));
+            if (&s == &s0 && it < n_timed) CU(cudaEventRecord(s0.ev_k[2 * it + 1], s.stream));
             if (h->transport == TSC_TRANSPORT_NCCL) {
                 k_reduce_replicas<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.acc, K, h->R, s.thetasum, s.st);
                 LAUNCH(h);
@@ -1490,7 +1497,7 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
     h->converged = fin.converged;
     h->em_done = true;
     h->kernel_ms.clear();
-    for (int it = 0; it < std::min(issued, fin.iter); ++it) {
+    for (int it = 0; it < std::min(std::min(issued, fin.iter), n_timed); ++it) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, s0.ev_k[2 * it], s0.ev_k[2 * it + 1]));
         h->kernel_ms.push_back(ms);

@@ -164,6 +164,7 @@ struct TileArgs {
     const double* inner_amb;   // LNL: pi*theta and pi inside log1p
     const double* inner_uni;
     double* partials;          // LNL: one partial sum per block
+    const LogTab* log_tab;     // LNL: table of log1p_big
 };
 
 // LONG8: compile the single-pass path for reads of 129..256 entries (8 per lane in registers).  It wins big when
@@ -174,7 +175,12 @@ __global__ void __launch_bounds__(kTileThreads, TSC_TILE_MINBLOCKS)
 k_tiles(const TileArgs a) {
     extern __shared__ double s_dyn[];
     __shared__ double s_red[32];
+    __shared__ LogTab s_log[MODE == TILE_LNL ? kLogTab : 1];
     if (a.st && a.st->done) return;
+    if (MODE == TILE_LNL) {
+        for (int i = threadIdx.x; i < kLogTab; i += blockDim.x) s_log[i] = a.log_tab[i];
+        __syncthreads();
+    }
     const Tile* __restrict__ tiles = a.tiles;
     const double* __restrict__ q = a.q;
     const int* __restrict__ col = a.col;
@@ -241,7 +247,7 @@ k_tiles(const TileArgs a) {
                         const double c = n8[i] * g;
                         if (MODE == TILE_FUSED) atomicAdd(my + c8[i], c);
                         if (MODE == TILE_Z) __stcs(a.z_out + p, c);
-                        if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p(__ldg(q + p) * __ldg(a.inner_amb + c8[i])); }
+                        if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p_big(__ldg(q + p) * __ldg(a.inner_amb + c8[i]), s_log); }
                     }
                 }
                 continue;
@@ -259,7 +265,7 @@ k_tiles(const TileArgs a) {
                     const double c = (qv * gather_pt<SMEM_TAB>(pt, s_tab, s_cols, cc)) * g;
                     if (MODE == TILE_FUSED) { if (c != 0.0) atomicAdd(my + cc, c); }
                     if (MODE == TILE_Z) __stcs(a.z_out + p, c);
-                    if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p(qv * __ldg(a.inner_amb + cc)); }
+                    if (MODE == TILE_LNL) { if (c != 0.0) lnl_local += c * log1p_big(qv * __ldg(a.inner_amb + cc), s_log); }
                 }
             }
             continue;
@@ -346,7 +352,7 @@ k_tiles(const TileArgs a) {
                     if (c != 0.0) {
                         const unsigned nxt = (e < 3) ? F[(e + 1) & 3] : 1u;
                         const bool uniq = ((F[e] & ((F[e] >> 1) | (nxt << 31))) >> lane) & 1u;
-                        lnl_local += c * log1p(qq[e] * __ldg((uniq ? a.inner_uni : a.inner_amb) + cc[e]));
+                        lnl_local += c * log1p_big(qq[e] * __ldg((uniq ? a.inner_uni : a.inner_amb) + cc[e]), s_log);
                     }
                 }
             }

@@ -358,28 +358,33 @@ def test_config2_full_size_against_oracle():
     tl.close()
 
 
-def test_config3_size_independent_properties():
-    """BASELINE.json config 3 size (10 M reads x 15 k loci, ~2e8 entries): invariants that need no CPU EM.
+def test_config3_full_size_against_oracle():
+    """BASELINE.json config 3 size (10 M reads x 15 k loci, ~2e8 entries): two EM iterations of the CPU oracle beside
+    the default (clustered-stream) path -- pi, theta, diffs, lnl to 1e-9, `exclude` counts after EM bit-exact -- plus
+    invariants that need no CPU EM:
       * pi and theta are proportions (pi_prior = 0): each sums to 1
-      * every ambiguous read's posterior row sums to 1 -> sum_j thetasum_j = ambig_wt, i.e. sum(theta) = 1 exactly as above
-      * reassign('all', initial) counts the stored entries per locus, reassign('unique') the single-hit reads (integers,
-        independent of EM) -> compared with numpy bincounts
-      * the rows kernel and the flat-tile kernel agree
-    """
+      * reassign('all', initial) counts the stored entries per locus, reassign('unique') the single-hit reads
+      * the flat-tile kernel agrees with the default path
+    (The 1-vs-2-GPU half of config 3 is test_one_process_per_gpu_matches_oracle / test_multi_gpu_in_process_matches_oracle
+    and the `parity` block of every bench line.)"""
     N, K = 10_000_000, 15000
     m = _matrix(N=N, K=K, avg=20, skew=False, seed=1003)
-    opts = Opts(max_iter=5, em_epsilon=-1)
-    a = _tl(m, opts, kernel="tiles")
-    a.em()
+    opts = Opts(max_iter=2, em_epsilon=-1)
+    a, o = _tl(m, opts), _oracle(m, opts)
+    a.em(); o.em()
+    assert a.n_iter == o.n_iter == 2
+    assert rel_err(a.pi, o.pi) < TIGHT and rel_err(a.theta, o.theta) < TIGHT and rel_err(a.diffs, o.diffs) < TIGHT
+    assert abs(a.lnl - o.lnl) <= TIGHT * abs(o.lnl)
+    ex = a.reassign_colsum("exclude")
+    assert np.array_equal(ex, o.reassign_colsum("exclude"))
     assert abs(a.pi.sum() - 1.0) < 1e-9 and abs(a.theta.sum() - 1.0) < 1e-9
-    assert a.n_iter == 5 and np.all(np.diff(a.diffs) < 0), "diff_est shrinks from the uniform start"
     lens = np.diff(m.indptr)
     assert np.array_equal(a.reassign_colsum("all", initial=True), np.bincount(m.indices, minlength=K).astype(np.uint64))
     uniq_rows = np.flatnonzero(lens == 1)
     assert np.array_equal(a.reassign_colsum("unique"), np.bincount(m.indices[m.indptr[uniq_rows]], minlength=K).astype(np.uint64))
-    ex = a.reassign_colsum("exclude")
-    assert ex.sum() <= N and ex.sum() >= int(0.9 * N)
-    b = _tl(m, opts, kernel="rows")
+    st = a.layout_stats()
+    assert st["stream_entries"] + st["residual_entries"] == int(lens[lens > 1].sum())
+    b = _tl(m, opts, kernel="tiles")
     b.em()
     assert rel_err(a.pi, b.pi) < 1e-9 and abs(a.lnl - b.lnl) <= 1e-10 * abs(a.lnl)
     assert np.array_equal(ex, b.reassign_colsum("exclude"))

@@ -148,7 +148,8 @@ struct Shard {
     unsigned char* ell_stream = nullptr;
     long long ell_bytes = 0, ell_slices = 0, ell_reads = 0, ell_entries = 0;
     int4* ell_index = nullptr;            // per slice record: offset / 16, first locus, T | last locus << 8, reads
-    int ell_grid = 0;
+    int ell_grid = 0, ell_grid_lnl = 0;
+    long long res_amb_rows = 0, res_amb_nnz = 0;   // the ambiguous part of the residual CSR (it also holds the unique reads)
     long long res_rows = 0, res_nnz = 0, res_n_tiles = 0, res_n_long = 0;
     long long* res_indptr = nullptr;
     int* res_col = nullptr;
@@ -266,6 +267,8 @@ static int launch_rows(int G, F&& f) {
 static Csr csr_of(const Shard& s) { return Csr{s.indptr, s.col, s.q, s.n_rows}; }
 
 static int launch_fused(tsc_handle* h, Shard& s, bool gated);
+static int launch_lnl_kernels(tsc_handle* h, Shard& s, const EmState* st, const double* ta, const double* tu,
+                              const double* ia, const double* iu, int* nparts_out);
 
 // ------------------------------------------------------------------------------------------------- tile launches
 template <int MODE>
@@ -639,9 +642,11 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
     DevBuf tmp;
     tmp.arena = arena;
     int* key = nullptr;
-    unsigned long long* counters = nullptr;       // [0] ambiguous reads, [1] their entries, [2] residual cursor
-    CU(tmp.alloc(&counters, 4));
-    CU(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 4, s.stream));
+    // [0] ambiguous reads, [1] their entries, [2] reads outside the stream (packed count | entries), [3] the ambiguous
+    // ones among them (packed), [4] append cursor
+    unsigned long long* counters = nullptr;
+    CU(tmp.alloc(&counters, 8));
+    CU(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 8, s.stream));
     const bool ell_ok = n_rows > 0 && (long long)K * (1 << kEllLenBits) < (1LL << 31);
     long long n_cand = 0;
     int* sorted = nullptr;
@@ -687,7 +692,9 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         long long total = 0;
         if ((rc = fetch_ll(s, rec_off + n_slices, &total))) return rc;
         int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ell_fused, 32, kEllSmem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ell<ELL_FUSED>, 32, kEllSmem));
+        int per_sm_lnl = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lnl, k_ell<ELL_LNL>, 32, ell_smem_bytes<ELL_LNL>()));
         const int warps = s.n_sm * std::max(per_sm, 1);
         const long long n_seg = (n_slices + 31) / 32;      // a warp's unit of work between two window flushes
         lap("  ell slices+scan");
@@ -701,11 +708,13 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         s.ell_bytes = total;
         s.ell_slices = n_slices;
         s.ell_grid = (int)std::min<long long>(n_seg, warps);
+        s.ell_grid_lnl = (int)std::min<long long>(n_seg, (long long)s.n_sm * std::max(per_sm_lnl, 1));
         lap("  ell fill");
     }
-    // ---- residual CSR: ambiguous reads without a slot in the stream (key < 0, or every ambiguous read when the
-    // stream could not be built).  Usually a handful: they are counted first and then appended in whatever order the
-    // atomics give -- the order of the residual's reads is irrelevant, only each read's entries stay together.
+    // ---- residual CSR: every read without a slot in the stream -- the unique reads (they add nothing to the M-step
+    // sums but take part in the log-likelihood) and the ambiguous reads that do not fit a slice (key < 0; all of them
+    // when the stream could not be built).  They are counted first and then appended in whatever order the atomics
+    // give: the order of the residual's reads is irrelevant, only each read's entries stay together.
     {
         const int g = grid_for(n_rows, 256, s.n_sm * 16);
         k_res_count<<<g, 256, 0, s.stream>>>(s.indptr, n_rows, key, counters);
@@ -717,8 +726,10 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         const long long amb_rows = (long long)cnt[0], amb_nnz = (long long)cnt[1];
         s.res_rows = (long long)(cnt[2] >> kResShift);
         s.res_nnz = (long long)(cnt[2] & ((1ULL << kResShift) - 1ULL));
-        s.ell_reads = amb_rows - s.res_rows;
-        s.ell_entries = amb_nnz - s.res_nnz;
+        s.res_amb_rows = (long long)(cnt[3] >> kResShift);
+        s.res_amb_nnz = (long long)(cnt[3] & ((1ULL << kResShift) - 1ULL));
+        s.ell_reads = amb_rows - s.res_amb_rows;
+        s.ell_entries = amb_nnz - s.res_amb_nnz;
         lap("  residual count");
         if (s.res_rows >= (1LL << (64 - kResShift))) return fail(TSC_ERR_ARG, "too many reads outside the slice stream on one GPU");
         if (s.res_rows > 0) {
@@ -729,8 +740,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
             CU(cudaMalloc(&s.res_wy, sizeof(double) * s.res_rows));
             CU(cudaMemsetAsync(s.res_col + s.res_nnz, 0, sizeof(int) * pad, s.stream));
             CU(cudaMemsetAsync(s.res_q + s.res_nnz, 0, sizeof(double) * pad, s.stream));
-            CU(cudaMemsetAsync(counters + 3, 0, sizeof(unsigned long long), s.stream));
-            k_res_append<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, key, counters + 3,
+            k_res_append<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, key, counters + 4,
                                                                                      s.res_indptr, s.res_col, s.res_q, s.res_wy);
             LAUNCH(h);
             CU(cudaMemcpyAsync(s.res_indptr + s.res_rows, &s.res_nnz, sizeof(long long), cudaMemcpyHostToDevice, s.stream));
@@ -1009,7 +1019,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         CU(cudaEventCreateWithFlags(&s.ev_poll[1], cudaEventDisableTiming));
         s.grid_rows = s.n_sm * 4;                   // 512-thread blocks, persistent grid-stride
         s.grid_tiles = s.n_sm * 2;                  // refined below from the occupancy of the tile kernel
-        CU(cudaMalloc(&s.partials, sizeof(double) * (s.n_sm * 32)));
+        CU(cudaMalloc(&s.partials, sizeof(double) * (s.n_sm * 64)));
         CU(cudaMalloc(&s.log_tab, sizeof(LogTab) * kLogTab));
         k_log_table<<<1, kLogTab, 0, s.stream>>>(s.log_tab);
         LAUNCH(h);
@@ -1031,7 +1041,8 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
     if (h->kernel == TSC_KERNEL_ELL) {
         for (auto& s : h->shards) {
             CU(cudaSetDevice(s.dev));
-            CU(cudaFuncSetAttribute(k_ell_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEllSmem));
+            CU(cudaFuncSetAttribute(k_ell<ELL_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEllSmem));
+            CU(cudaFuncSetAttribute(k_ell<ELL_LNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ell_smem_bytes<ELL_LNL>()));
             Arena arena;
             {   // the raw uploads are dead once Q is built: their memory serves the temporaries of the clustering
                 const int i = (int)(&s - &h->shards[0]);
@@ -1215,7 +1226,7 @@ extern "C" int tsc_get_layout_stats(tsc_handle* h, int64_t* out8) {
     if (!h || !out8) return fail(TSC_ERR_ARG, "NULL argument");
     const Shard& s = h->shards[0];
     out8[0] = s.ell_bytes; out8[1] = s.ell_slices; out8[2] = s.ell_reads; out8[3] = s.ell_entries;
-    out8[4] = s.res_rows; out8[5] = s.res_nnz; out8[6] = s.ell_grid; out8[7] = s.n_tiles;
+    out8[4] = s.res_amb_rows; out8[5] = s.res_amb_nnz; out8[6] = s.ell_grid; out8[7] = s.n_tiles;
     return TSC_OK;
 }
 
@@ -1287,10 +1298,12 @@ extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float
                 a.tab_amb = ta; a.tab_uni = tu; a.z_out = zd;
                 launch_tiles<TILE_Z>(s, a, false);
                 break;
-            case 2:
-                a.tab_amb = ta; a.tab_uni = tu; a.inner_amb = s.pt; a.inner_uni = s.pi; a.partials = s.partials; a.log_tab = s.log_tab;
-                launch_tiles<TILE_LNL>(s, a, false);
-                break;
+            case 2: {
+                int np = 0;
+                const long long l0 = h->launches;
+                if (launch_lnl_kernels(h, s, nullptr, ta, tu, s.pt, s.pi, &np)) err = cudaErrorUnknown;
+                h->launches = l0;             // counted below
+            } break;
             case 3: {
                 ReassignArgs g{TSC_EXCLUDE, 0.9, nullptr, nullptr, s.colsum, nullptr};
                 launch_rows(h->G, [&](auto gg) {
@@ -1336,11 +1349,11 @@ static int launch_fused(tsc_handle* h, Shard& s, bool gated) {
     } else if (h->kernel == TSC_KERNEL_ELL) {
         // the clustered stream, then whatever does not fit a slice through the flat tiles of the residual CSR
         if (s.ell_slices > 0) {
-            EllArgs e{s.ell_stream, s.ell_index, s.ell_slices, s.pt, s.acc, h->K, h->R, st};
-            k_ell_fused<<<s.ell_grid, 32, kEllSmem, s.stream>>>(e);
+            EllArgs e{s.ell_stream, s.ell_index, s.ell_slices, s.pt, s.acc, h->K, h->R, st, nullptr, nullptr, nullptr};
+            k_ell<ELL_FUSED><<<s.ell_grid, 32, kEllSmem, s.stream>>>(e);
             LAUNCH(h);
         }
-        if (s.res_rows > 0) {
+        if (s.res_amb_rows > 0) {         // (a residual of unique reads only has nothing to add)
             TileArgs a{};
             a.tiles = s.res_tiles; a.n_tiles = s.res_n_tiles; a.q = s.res_q; a.col = s.res_col; a.wy = s.res_wy; a.tab_amb = s.pt;
             a.acc = s.acc; a.K = h->K; a.R = h->R; a.s_cols = 0; a.st = st;
@@ -1359,6 +1372,39 @@ static int launch_fused(tsc_handle* h, Shard& s, bool gated) {
 }
 
 // global log-likelihood into s.scalars[4] of every shard (model.py:744-760)
+// One shard's log-likelihood with z regenerated from the E-step tables (ta, tu) and `inner` inside log1p: per-CTA
+// partials into s.partials, returns how many.  Clustered-stream layout: the stream kernel for its reads, the flat
+// tiles of the residual CSR for everybody else; otherwise the flat tiles of the whole shard.
+static int launch_lnl_kernels(tsc_handle* h, Shard& s, const EmState* st, const double* ta, const double* tu,
+                              const double* ia, const double* iu, int* nparts_out) {
+    int nparts = 0;
+    TileArgs a{};
+    a.tab_amb = ta; a.tab_uni = tu; a.inner_amb = ia; a.inner_uni = iu; a.K = h->K; a.st = st; a.log_tab = s.log_tab;
+    if (h->kernel == TSC_KERNEL_ELL) {
+        if (s.ell_slices > 0) {
+            EllArgs e{s.ell_stream, s.ell_index, s.ell_slices, ta, nullptr, h->K, 1, st, ia, s.partials, s.log_tab};
+            k_ell<ELL_LNL><<<s.ell_grid_lnl, 32, ell_smem_bytes<ELL_LNL>(), s.stream>>>(e);
+            LAUNCH(h);
+            nparts = s.ell_grid_lnl;
+        }
+        if (s.res_rows > 0) {
+            a.tiles = s.res_tiles; a.n_tiles = s.res_n_tiles; a.q = s.res_q; a.col = s.res_col; a.partials = s.partials + nparts;
+            launch_tiles<TILE_LNL>(s, a, false, s.res_n_long * 200 > s.res_n_tiles ? 1 : 0);
+            LAUNCH(h);
+            nparts += s.grid_tiles;
+        }
+    } else {
+        a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.partials = s.partials;
+        launch_tiles<TILE_LNL>(s, a, false);
+        LAUNCH(h);
+        nparts = s.grid_tiles;
+    }
+    CU(cudaGetLastError());
+    *nparts_out = nparts;
+    return TSC_OK;
+}
+
+// global log-likelihood into s.scalars[4] of every shard (model.py:744-760)
 static int launch_lnl(tsc_handle* h, const double* (*zin_of)(Shard&), bool from_prev, bool gated,
                       const double* (*ia)(Shard&), const double* (*iu)(Shard&)) {
     for (auto& s : h->shards) {
@@ -1367,20 +1413,16 @@ static int launch_lnl(tsc_handle* h, const double* (*zin_of)(Shard&), bool from_
         const EmState* st = gated ? s.st : nullptr;
         int nparts = s.grid_rows;
         if (!zin && h->kernel != TSC_KERNEL_ROWS) {
-            TileArgs a{};
-            a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col;
-            a.tab_amb = s.pt_prev; a.tab_uni = s.pi_prev; a.inner_amb = ia(s); a.inner_uni = iu(s);
-            a.K = h->K; a.st = st; a.partials = s.partials; a.log_tab = s.log_tab;
-            nparts = s.grid_tiles;
-            launch_tiles<TILE_LNL>(s, a, false);
+            int rc = launch_lnl_kernels(h, s, st, s.pt_prev, s.pi_prev, ia(s), iu(s), &nparts);
+            if (rc) return rc;
         } else {
             launch_rows(h->G, [&](auto g) {
                 k_lnl_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(
                     csr_of(s), zin, from_prev ? s.pt_prev : nullptr, from_prev ? s.pi_prev : nullptr, ia(s), iu(s), s.partials, st);
             });
+            LAUNCH(h);
+            CU(cudaGetLastError());
         }
-        LAUNCH(h);
-        CU(cudaGetLastError());
         // (when the loop is already done the partials are stale; k_lnl_control ignores the value)
         k_sum_partials<<<1, 1024, 0, s.stream>>>(s.partials, nparts, s.scalars + 4);
         LAUNCH(h);

@@ -46,7 +46,6 @@ constexpr int kEllHdr = kEllReads * 8;        // wy
 #endif
 constexpr int kEllAhead = TSC_ELL_AHEAD;      // records between the L2 prefetch and the loads
 constexpr int kEllLenBits = 6;                // sort key = first locus << 6 | snake(length)
-constexpr size_t kEllSmem = sizeof(double) * ((kEllWin + 1) * kEllReads + kEllWin + 8);
 static_assert(2 * kEllTMax < (1 << kEllLenBits), "length must fit the key");
 static_assert(kEllTMax == 24, "k_ell_fused dispatches bodies of 4..24 steps");
 static_assert(kEllAhead >= 1 && kEllAhead < 32, "prefetch distance is within one segment");
@@ -229,32 +228,36 @@ __global__ void __launch_bounds__(256) k_ell_fill(const long long* __restrict__ 
     }
 }
 
-// Residual CSR = ambiguous reads that are not in the stream (key < 0; key == nullptr: every ambiguous read).
-// counters[0] += ambiguous reads, [1] += their entries, [2] += (1 << kResShift | entries) per residual read.
+// Residual CSR = the reads that are not in the stream: key < 0 (key == nullptr: everybody), unique reads included.
+// counters[0] += ambiguous reads, [1] += their entries, [2] += (1 << kResShift | entries) per residual read,
+// [3] += the same for the ambiguous residual reads.
 constexpr int kResShift = 38;     // a cursor packs (reads << 38 | entries): < 2^26 reads and < 2^38 entries per GPU
 
 __global__ void k_res_count(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ key,
                             unsigned long long* __restrict__ counters) {
-    unsigned long long rows = 0, ents = 0, res = 0;
+    unsigned long long rows = 0, ents = 0, res = 0, res_amb = 0;
     long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; r < n_rows; r += stride) {
         const long long len = ip[r + 1] - ip[r];
-        if (len < 2) continue;
-        ++rows;
-        ents += (unsigned long long)len;
-        if (key == nullptr || key[r] < 0) res += (1ULL << kResShift) | (unsigned long long)len;
+        if (len >= 2) { ++rows; ents += (unsigned long long)len; }
+        if (key == nullptr || key[r] < 0) {
+            res += (1ULL << kResShift) | (unsigned long long)len;
+            if (len >= 2) res_amb += (1ULL << kResShift) | (unsigned long long)len;
+        }
     }
-    // warp totals first: three atomics per warp
+    // warp totals first: four atomics per warp
     for (int o = 16; o > 0; o >>= 1) {
         rows += __shfl_xor_sync(0xffffffffu, rows, o);
         ents += __shfl_xor_sync(0xffffffffu, ents, o);
         res += __shfl_xor_sync(0xffffffffu, res, o);
+        res_amb += __shfl_xor_sync(0xffffffffu, res_amb, o);
     }
     if ((threadIdx.x & 31) == 0) {
         if (rows) atomicAdd(counters + 0, rows);
         if (ents) atomicAdd(counters + 1, ents);
         if (res) atomicAdd(counters + 2, res);
+        if (res_amb) atomicAdd(counters + 3, res_amb);
     }
 }
 
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict_
     for (; r < r_end; r += stride) {
         long long b = 0, e = 0;
         bool res = false;
-        if (r < n_rows) { b = ip[r]; e = ip[r + 1]; res = (e - b >= 2) && (key == nullptr || key[r] < 0); }
+        if (r < n_rows) { b = ip[r]; e = ip[r + 1]; res = (key == nullptr || key[r] < 0); }
         unsigned long long old = 0;
         if (res && lane == 0) old = atomicAdd(cursor, (1ULL << kResShift) | (unsigned long long)(e - b));
         old = __shfl_sync(gmask, old, (threadIdx.x & 31) & ~7);
@@ -285,17 +288,33 @@ __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// the per-iteration kernel
+// the stream kernels
 // ---------------------------------------------------------------------------------------------------------------
+// What a pass over the stream produces.
+//   ELL_FUSED : E-step + M-step sums (the per-iteration kernel; model.py:718-722 + 730-733)
+//   ELL_LNL   : log-likelihood of the stream's reads, sum z * log1p(Q * inner[locus]) with z from the E-step table
+//               (model.py:744-760); the reads outside the stream go through k_tiles<TILE_LNL> on the residual CSR
+enum { ELL_FUSED = 0, ELL_LNL = 1 };
+
 struct EllArgs {
     const unsigned char* stream;
     const int4* index;            // per record: byte offset / 16, lo, T | hi << 8, reads
     long long n_slices;
-    const double* pt;             // pi*theta
-    double* acc;                  // R replicas of K doubles
+    const double* pt;             // pi*theta of the E-step (every read of the stream is ambiguous)
+    double* acc;                  // FUSED: R replicas of K doubles
     int K, R;
     const EmState* st;            // nullptr = always run
+    const double* inner;          // LNL: pi*theta inside log1p
+    double* partials;             // LNL: one partial sum per CTA
+    const LogTab* log_tab;        // LNL
 };
+
+template <int MODE>
+__host__ __device__ constexpr size_t ell_smem_bytes() {
+    return MODE == ELL_FUSED ? sizeof(double) * ((kEllWin + 1) * kEllReads + kEllWin + 8)
+                             : sizeof(double) * 2 * (kEllWin + 8) + sizeof(LogTab) * kLogTab;
+}
+constexpr size_t kEllSmem = ell_smem_bytes<ELL_FUSED>();
 
 __device__ __forceinline__ void ell_prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -306,16 +325,34 @@ __device__ __forceinline__ double ell_ld_stream(const double* p) {      // read 
     return v;
 }
 
-// One slice record, TM = T rounded up to a multiple of 4: straight-line code, every load of the slice is in flight at
-// once; only the last three steps are conditional.
-template <int TM>
-__device__ __forceinline__ void ell_body(const unsigned char* __restrict__ rec, int T, int lane, const double* s_pt,
-                                         unsigned char* accb /* s_acc + 8 * (lane & 15) */) {
-    const double w_mine = __ldg(reinterpret_cast<const double*>(rec) + (lane & 15));
+// LNL, out of line and practically never taken: the terms of a slice whose log1p argument is below 2^53 (or not
+// finite), recomputed from the record with the library log1p.  Kept away from the main body's registers.
+__device__ __noinline__ double ell_lnl_slow(const unsigned char* __restrict__ rec, int T, int lane, const double* s_pt,
+                                            const double* s_in, double rr) {
     const unsigned char* cp = rec + kEllHdr + lane;
     const double* qp = reinterpret_cast<const double*>(rec + kEllHdr + 32 * T) + lane;
+    double out = 0.0;
+    for (int t = 0; t < T; ++t) {
+        const unsigned jw = cp[32 * t];
+        const double qv = qp[32 * t];
+        const double z = (qv * s_pt[jw]) * rr, xt = qv * s_in[jw];
+        if (z != 0.0 && !log_big_ok(xt)) out += z * log1p(xt);
+    }
+    return out;
+}
+
+// One slice record, TM = T rounded up to a multiple of 4: straight-line code, every load of the slice is in flight at
+// once; only the last three steps are conditional.
+template <int MODE, int TM>
+__device__ __forceinline__ void ell_body(const unsigned char* __restrict__ rec, int T, int lane, const double* s_pt,
+                                         unsigned char* accb /* FUSED: s_acc + 8 * (lane & 15) */,
+                                         const double* s_in, const LogTab* s_log, double& lnl_local) {
+    const unsigned char* cp = rec + kEllHdr + lane;
+    const double* qp = reinterpret_cast<const double*>(rec + kEllHdr + 32 * T) + lane;
+    double w_mine = 1.0;
+    if (MODE == ELL_FUSED) w_mine = __ldg(reinterpret_cast<const double*>(rec) + (lane & 15));
     double n[TM];
-    unsigned ao[TM];              // window row of the entry, then byte offset of its accumulator row
+    unsigned ao[TM];              // window row of the entry, then (FUSED) byte offset of its accumulator row
 #pragma unroll
     for (int t = 0; t < TM; ++t) {
         n[t] = 0.0;
@@ -326,31 +363,57 @@ __device__ __forceinline__ void ell_body(const unsigned char* __restrict__ rec, 
         }
     }
     // ---- pass 1: numerators n = Q * (pi*theta)[locus], private row sum
+    double x[MODE == ELL_LNL ? TM : 1];               // LNL: the argument of log1p, Q * inner[locus]
     double sp[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int t = 0; t < TM; ++t) {
+        if (MODE == ELL_LNL) x[t] = n[t] * s_in[ao[t]];
         n[t] *= s_pt[ao[t]];
         sp[t & 3] += n[t];
-        ao[t] *= kEllReads * 8;
+        if (MODE == ELL_FUSED) ao[t] *= kEllReads * 8;
     }
     double sum = (sp[0] + sp[1]) + (sp[2] + sp[3]);
     sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-    // (w*Y) * recip0(total), the same expression as the tile kernel; empty read slots have w = 0
-    const double g = (w_mine != 0.0) ? w_mine * recip0(sum) : 0.0;
-    // ---- pass 2: c = n * g into this read slot's private accumulator column.  Loci are unique within a read, the two
-    // lanes of a read hold different entries, and empty slots point at the dummy row, so no two real updates of a
-    // slice share an address: all loads may precede all stores.
+    if (MODE == ELL_FUSED) {
+        // (w*Y) * recip0(total), the same expression as the tile kernel; empty read slots have w = 0
+        const double g = (w_mine != 0.0) ? w_mine * recip0(sum) : 0.0;
+        // ---- pass 2: c = n * g into this read slot's private accumulator column.  Loci are unique within a read, the
+        // two lanes of a read hold different entries, and empty slots point at the dummy row, so no two real updates of
+        // a slice share an address: all loads may precede all stores.
 #pragma unroll
-    for (int t = 0; t < TM; ++t) n[t] = *reinterpret_cast<const double*>(accb + ao[t]) + n[t] * g;
+        for (int t = 0; t < TM; ++t) n[t] = *reinterpret_cast<const double*>(accb + ao[t]) + n[t] * g;
 #pragma unroll
-    for (int t = 0; t < TM; ++t) *reinterpret_cast<double*>(accb + ao[t]) = n[t];
+        for (int t = 0; t < TM; ++t) *reinterpret_cast<double*>(accb + ao[t]) = n[t];
+    } else {
+        // straight-line: every entry takes the table-driven log; entries whose argument is outside its range (never,
+        // in practice) are redone with the library log1p afterwards
+        const double rr = recip0(sum);
+        double acc[2] = {0.0, 0.0};
+        bool slow = false;
+#pragma unroll
+        for (int t = 0; t < TM; ++t) {
+            const double xt = x[MODE == ELL_LNL ? t : 0];
+            n[t] *= rr;                                           // z
+            const double term = n[t] * log_big_core(xt, s_log);
+            const bool use = n[t] != 0.0, ok = log_big_ok(xt);
+            acc[t & 1] += (use && ok) ? term : 0.0;
+            slow = slow || (use && !ok);
+        }
+        lnl_local += acc[0] + acc[1];
+        if (__any_sync(0xffffffffu, slow)) lnl_local += ell_lnl_slow(rec, T, lane, s_pt, s_in, rr);
+    }
 }
 
-__global__ void __launch_bounds__(32) k_ell_fused(const EllArgs a) {
+template <int MODE>
+__global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     if (a.st && a.st->done) return;
-    double* s_acc = reinterpret_cast<double*>(s_raw);                     // [kEllWin + 1][kEllReads]; last row = dummy
-    double* s_pt = s_acc + (kEllWin + 1) * kEllReads;                    // [kEllWin + 8]; [kEllWin] = 0 for empty slots
+    // FUSED: s_acc [kEllWin + 1][kEllReads] (last row = dummy) | s_pt [kEllWin + 8] ([kEllWin] = 0 for empty slots)
+    // LNL:   s_pt [kEllWin + 8] | s_in [kEllWin + 8] | log table
+    double* s_acc = reinterpret_cast<double*>(s_raw);
+    double* s_pt = (MODE == ELL_FUSED) ? s_acc + (kEllWin + 1) * kEllReads : s_acc;
+    double* s_in = s_pt + kEllWin + 8;
+    LogTab* s_log = reinterpret_cast<LogTab*>(s_in + kEllWin + 8);
     const int lane = threadIdx.x;
     const int nw = gridDim.x;
     const long long n_slices = a.n_slices;
@@ -358,10 +421,15 @@ __global__ void __launch_bounds__(32) k_ell_fused(const EllArgs a) {
     const int K = a.K;
     const double* __restrict__ pt = a.pt;
     const unsigned char* __restrict__ stream = a.stream;
-    double* my = a.acc + (size_t)(blockIdx.x % a.R) * K;
+    double* my = (MODE == ELL_FUSED) ? a.acc + (size_t)(blockIdx.x % a.R) * K : nullptr;
     unsigned char* accb = reinterpret_cast<unsigned char*>(s_acc) + 8 * (lane & 15);
+    double lnl_local = 0.0;
 
-    for (int i = lane; i < (kEllWin + 1) * kEllReads + kEllWin + 8; i += 32) s_acc[i] = 0.0;     // accumulators, s_pt
+    for (int i = lane; i < (int)(ell_smem_bytes<MODE>() / 8); i += 32) s_acc[i] = 0.0;     // accumulators, tables
+    if (MODE == ELL_LNL) {
+        __syncwarp();
+        for (int i = lane; i < kLogTab; i += 32) s_log[i] = a.log_tab[i];
+    }
     __syncwarp();
 
     // lane l of a segment's index registers describes record 32*seg + l (T = 0 beyond the end)
@@ -413,32 +481,41 @@ __global__ void __launch_bounds__(32) k_ell_fused(const EllArgs a) {
                 __syncwarp();
                 int first_new = lb;
                 if (Fb >= 0) {
-                    const int e = min(lb, Fb + 4);
-                    for (int b = Fb; b < e; ++b) flush_block(b);
+                    if (MODE == ELL_FUSED) {
+                        const int e = min(lb, Fb + 4);
+                        for (int b = Fb; b < e; ++b) flush_block(b);
+                    }
                     first_new = max(lb, Fb + 4);
                 }
                 for (int b = first_new; b < lb + 4; ++b) {
                     const int j = b * 32 + lane;
                     s_pt[(b & 3) * 32 + lane] = (j < K) ? __ldg(pt + j) : 0.0;
+                    if (MODE == ELL_LNL) s_in[(b & 3) * 32 + lane] = (j < K) ? __ldg(a.inner + j) : 0.0;
                 }
                 Fb = lb;
                 __syncwarp();
             }
             switch ((T + 3) >> 2) {
-                case 1: ell_body<4>(rec, T, lane, s_pt, accb); break;
-                case 2: ell_body<8>(rec, T, lane, s_pt, accb); break;
-                case 3: ell_body<12>(rec, T, lane, s_pt, accb); break;
-                case 4: ell_body<16>(rec, T, lane, s_pt, accb); break;
-                case 5: ell_body<20>(rec, T, lane, s_pt, accb); break;
-                default: ell_body<24>(rec, T, lane, s_pt, accb); break;
+                case 1: ell_body<MODE, 4>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
+                case 2: ell_body<MODE, 8>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
+                case 3: ell_body<MODE, 12>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
+                case 4: ell_body<MODE, 16>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
+                case 5: ell_body<MODE, 20>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
+                default: ell_body<MODE, 24>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
             }
         }
         cur = nxt;
         nxt = after;
-        // ---- segment done: hand the window to the global accumulator
-        __syncwarp();
-        if (Fb >= 0) for (int b = Fb; b < Fb + 4; ++b) flush_block(b);
-        Fb = -1;
+        if (MODE == ELL_FUSED) {
+            // ---- segment done: hand the window to the global accumulator
+            __syncwarp();
+            if (Fb >= 0) for (int b = Fb; b < Fb + 4; ++b) flush_block(b);
+            Fb = -1;
+        }
+    }
+    if (MODE == ELL_LNL) {
+        lnl_local = group_sum<32>(lnl_local, 0xffffffffu);
+        if (lane == 0) a.partials[blockIdx.x] = lnl_local;
     }
 }
 

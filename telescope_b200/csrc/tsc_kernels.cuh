@@ -60,8 +60,8 @@ __global__ void k_log_table(LogTab* __restrict__ tab) {
     tab[i].l = -log(c);
 }
 
-__device__ __forceinline__ double log1p_big(double x, const LogTab* __restrict__ s_tab) {
-    if (!(x >= 9007199254740992.0) || x > 1.7e308) return log1p(x);     // < 2^53, NaN, inf
+// branch-free core: log(x) for finite x >= 2^53 (any other bit pattern gives a harmless garbage value)
+__device__ __forceinline__ double log_big_core(double x, const LogTab* __restrict__ s_tab) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const int e = (hi >> 20) - 1023;
     const LogTab t = s_tab[(hi >> 13) & (kLogTab - 1)];
@@ -75,6 +75,12 @@ __device__ __forceinline__ double log1p_big(double x, const LogTab* __restrict__
     const double ed = (double)e;
     // ln2 split: the high part has 11 trailing zero bits, so e * hi is exact
     return fma(ed, 6.93147180369123816490e-01, t.l) + fma(ed, 1.90821492927058770002e-10, p);
+}
+__device__ __forceinline__ bool log_big_ok(double x) { return x >= 9007199254740992.0 && x <= 1.7e308; }   // 2^53 .. finite
+
+__device__ __forceinline__ double log1p_big(double x, const LogTab* __restrict__ s_tab) {
+    if (!log_big_ok(x)) return log1p(x);
+    return log_big_core(x, s_tab);
 }
 
 template <int G>

@@ -472,6 +472,31 @@ def test_ell_stream_boundaries(K):
     tl.close(); t2.close()
 
 
+@pytest.mark.parametrize("kernel", ["ell", "tiles"])
+def test_small_scores_take_the_library_log1p(kernel):
+    """The log-likelihood pass uses a table-driven log for arguments >= 2^53 (every realistic score) and the library
+    log1p below: scores spread over 1..300 put Q * pi * theta on both sides of the switch, inside single slices."""
+    rng = np.random.default_rng(17)
+    N, K = 30000, 200
+    lens = rng.integers(1, 14, N)
+    rows = [np.sort(rng.choice(np.arange(f, min(K, f + 30)), min(n, min(K, f + 30) - f), replace=False))
+            for f, n in zip(rng.integers(0, K - 1, N), lens)]
+    lens = np.array([len(r) for r in rows])
+    indptr = np.concatenate(([0], np.cumsum(lens)))
+    indices = np.concatenate(rows).astype(np.int32)
+    raw = rng.integers(1, 301, indices.size).astype(np.uint16)
+    m = sp.csr_matrix((raw, indices, indptr), shape=(N, K))
+    opts = Opts(max_iter=6, em_epsilon=-1)
+    tl, o = _tl(m, opts, kernel=kernel), _oracle(m, opts)
+    tl.em(use_likelihood=True); o.em(use_likelihood=True)
+    assert tl.n_iter == o.n_iter
+    assert rel_err(tl.lnls, o.lnls) < TIGHT and abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
+    assert rel_err(tl.pi, o.pi) < TIGHT
+    x = o.Q * (o.pi * o.theta)[o.indices]
+    assert (x < 2.0 ** 53).mean() > 0.05 and (x >= 2.0 ** 53).mean() > 0.05, "both branches must be exercised"
+    tl.close()
+
+
 def test_ell_handles_unsorted_columns_through_the_residual_path():
     """Non-canonical CSR (loci not increasing inside a read) must not enter a slice: the stream relies on distinct,
     increasing loci per read."""

@@ -134,6 +134,14 @@ struct Shard {
     int grid_rows = 0, grid_tiles = 0;
     size_t smem_tiles = 0;
     int s_cols = 0;
+    // device memory comes in a few slabs (one cudaMalloc each: allocation calls cost milliseconds and their cost
+    // varies wildly); the array pointers of this struct point into them unless allocated on their own
+    std::vector<std::pair<char*, size_t>> slabs;
+    bool in_slab(const void* p) const {
+        for (auto& b : slabs) if ((const char*)p >= b.first && (const char*)p < b.first + b.second) return true;
+        return false;
+    }
+    uint16_t* raw = nullptr;                    // uploaded scores; after construction: scratch of the clustering
     // peer-memory transport (tsc_peer.cuh): this GPU's exchange buffer, every rank's buffer as mapped here
     unsigned char* peer_own = nullptr;
     std::vector<unsigned char*> peer_map;       // world entries; [world_rank] == peer_own
@@ -336,7 +344,8 @@ static void free_shard(Shard& s) {
                     s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad,
                     s.ell_stream, s.ell_index, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles,
                     s.peer_ptrs_d, s.tail_partials, s.tail_ticket, s.peer_err, s.log_tab};
-    for (void* p : ptrs) if (p) cudaFree(p);
+    for (void* p : ptrs) if (p && !s.in_slab(p)) cudaFree(p);
+    for (auto& b : s.slabs) cudaFree(b.first);
     for (size_t r = 0; r < s.peer_map.size(); ++r)
         if (r < s.peer_opened.size() && s.peer_opened[r] && s.peer_map[r]) cudaIpcCloseMemHandle(s.peer_map[r]);
     if (s.peer_own) cudaFree(s.peer_own);
@@ -569,10 +578,29 @@ struct DevBuf {              // device temporaries released on every exit path
     bool owns(void* q) const { return std::find(p.begin(), p.end(), q) != p.end(); }
 };
 
+struct SlabPlan {            // sizes first, one cudaMalloc, then the pointers
+    struct Item { void** out; size_t bytes; };
+    std::vector<Item> items;
+    template <typename T> void add(T** out, size_t n) { items.push_back({(void**)out, std::max<size_t>(n, 1) * sizeof(T)}); }
+    int commit(Shard& s) {
+        size_t total = 0;
+        for (auto& it : items) total += (it.bytes + 255) & ~(size_t)255;
+        char* base = nullptr;
+        CU(cudaMalloc(&base, std::max<size_t>(total, 256)));
+        s.slabs.push_back({base, std::max<size_t>(total, 256)});
+        size_t off = 0;
+        for (auto& it : items) { *it.out = base + off; off += (it.bytes + 255) & ~(size_t)255; }
+        return TSC_OK;
+    }
+};
+
 static int build_tiles(tsc_handle* h, Shard& s, const long long* indptr_d, long long n_rows, Tile** tiles_out,
-                       long long* n_tiles_out, long long* n_long_out) {
+                       long long* n_tiles_out, long long* n_long_out, Arena* arena = nullptr) {
     const int n_chunks = (int)((n_rows + kChunkRows - 1) / kChunkRows);
     DevBuf tmp;
+    tmp.arena = arena;
+    Arena mark;
+    if (arena) mark = *arena;
     int* counts_d = nullptr;
     long long* offs_d = nullptr;
     unsigned long long* nlong_d = nullptr;
@@ -603,6 +631,7 @@ static int build_tiles(tsc_handle* h, Shard& s, const long long* indptr_d, long 
     CU(cudaMemcpyAsync(&nl, nlong_d, sizeof(nl), cudaMemcpyDeviceToHost, s.stream));
     CU(cudaStreamSynchronize(s.stream));
     *n_long_out = (long long)nl;
+    if (arena) arena->off = mark.off;
     return TSC_OK;
 }
 
@@ -734,10 +763,15 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         if (s.res_rows >= (1LL << (64 - kResShift))) return fail(TSC_ERR_ARG, "too many reads outside the slice stream on one GPU");
         if (s.res_rows > 0) {
             const size_t pad = 256;
-            CU(cudaMalloc(&s.res_indptr, sizeof(long long) * (s.res_rows + 1)));
-            CU(cudaMalloc(&s.res_col, sizeof(int) * (s.res_nnz + pad)));
-            CU(cudaMalloc(&s.res_q, sizeof(double) * (s.res_nnz + pad)));
-            CU(cudaMalloc(&s.res_wy, sizeof(double) * s.res_rows));
+            {
+                SlabPlan rs;
+                rs.add(&s.res_indptr, (size_t)s.res_rows + 1);
+                rs.add(&s.res_col, (size_t)s.res_nnz + pad);
+                rs.add(&s.res_q, (size_t)s.res_nnz + pad);
+                rs.add(&s.res_wy, (size_t)s.res_rows);
+                int rc = rs.commit(s);
+                if (rc) return rc;
+            }
             CU(cudaMemsetAsync(s.res_col + s.res_nnz, 0, sizeof(int) * pad, s.stream));
             CU(cudaMemsetAsync(s.res_q + s.res_nnz, 0, sizeof(double) * pad, s.stream));
             k_res_append<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, key, counters + 4,
@@ -746,7 +780,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
             CU(cudaMemcpyAsync(s.res_indptr + s.res_rows, &s.res_nnz, sizeof(long long), cudaMemcpyHostToDevice, s.stream));
             CU(cudaGetLastError());
             CU(cudaStreamSynchronize(s.stream));
-            int rc = build_tiles(h, s, s.res_indptr, s.res_rows, &s.res_tiles, &s.res_n_tiles, &s.res_n_long);
+            int rc = build_tiles(h, s, s.res_indptr, s.res_rows, &s.res_tiles, &s.res_n_tiles, &s.res_n_long, arena);
             if (rc) return rc;
             lap("  residual copy+tiles");
         }
@@ -858,34 +892,47 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
     std::vector<int*> colin_d(n_local, nullptr);
     std::vector<unsigned long long*> cnt_d(n_local, nullptr);
     std::vector<double*> lut_d(n_local, nullptr);
-    auto cleanup_tmp = [&]() {
-        for (int i = 0; i < n_local; ++i) {
-            cudaSetDevice(h->shards[i].dev);
-            if (raw_d[i]) cudaFree(raw_d[i]);
-            if (colin_d[i]) cudaFree(colin_d[i]);
-            if (cnt_d[i]) cudaFree(cnt_d[i]);
-            if (lut_d[i]) cudaFree(lut_d[i]);
-            raw_d[i] = nullptr; colin_d[i] = nullptr; cnt_d[i] = nullptr; lut_d[i] = nullptr;
-        }
-    };
-    struct TmpGuard { std::function<void()> f; ~TmpGuard() { f(); } };
-    TmpGuard guard{cleanup_tmp};
+    auto cleanup_tmp = [&]() {};            // every temporary of this function lives in a slab of its shard
 
     const size_t pad = 256;
+    const bool permute = cfg.permute_columns != 0;
     for (int i = 0; i < n_local; ++i) {
         Shard& s = h->shards[i];
         CU(cudaSetDevice(s.dev));
-        CU(cudaMalloc(&s.indptr, sizeof(long long) * (s.n_rows + 1)));
-        CU(cudaMalloc(&s.col, sizeof(int) * (s.nnz + pad)));
-        CU(cudaMalloc(&s.q, sizeof(double) * (s.nnz + pad)));
-        CU(cudaMalloc(&s.wy, sizeof(double) * std::max<long long>(s.n_rows, 1)));
-        CU(cudaMalloc(&raw_d[i], sizeof(uint16_t) * std::max<long long>(s.nnz, 1)));
-        CU(cudaMalloc(&colin_d[i], sizeof(int) * std::max<long long>(s.nnz, 1)));
-        CU(cudaMalloc(&cnt_d[i], sizeof(unsigned long long) * K * 4));
-        CU(cudaMalloc(&lut_d[i], sizeof(double) * lut_len));
-        CU(cudaMalloc(&s.bad, sizeof(int)));
-        CU(cudaMemsetAsync(s.bad, 0, sizeof(int), s.stream));
-        CU(cudaMemsetAsync(cnt_d[i], 0, sizeof(unsigned long long) * K * 4, s.stream));
+        {
+            // one slab for the entry arrays.  Without a locus renumbering the caller's loci are uploaded straight into
+            // their final array; the raw scores stay (2 B per entry) and serve as scratch of the clustering afterwards
+            SlabPlan big;
+            big.add(&s.indptr, (size_t)s.n_rows + 1);
+            big.add(&s.col, (size_t)s.nnz + pad);
+            big.add(&s.q, (size_t)s.nnz + pad);
+            big.add(&s.wy, (size_t)s.n_rows);
+            big.add(&s.raw, (size_t)s.nnz);
+            if (permute) big.add(&colin_d[i], (size_t)s.nnz);
+            int rc = big.commit(s);
+            if (rc) return rc;
+            raw_d[i] = s.raw;
+            if (!permute) colin_d[i] = s.col;
+            // ... and one for everything K-sized
+            SlabPlan small;
+            const size_t kk = (size_t)K;
+            double** kv[] = {&s.pi, &s.theta, &s.pt, &s.pi_prev, &s.theta_prev, &s.pt_prev, &s.pi_init, &s.theta_init,
+                             &s.pisum0, &s.thetasum, &s.ones, &s.tmp_a, &s.tmp_b, &s.tmp_c, &s.colsum};
+            for (double** p : kv) small.add(p, kk);
+            small.add(&s.acc, kk * h->R);
+            small.add(&s.perm, kk);
+            small.add(&cnt_d[i], kk * 4);
+            small.add(&lut_d[i], (size_t)lut_len);
+            small.add(&s.bad, 1);
+            small.add(&s.consts, 1);
+            small.add(&s.st, 1);
+            small.add(&s.scalars, 8);
+            small.add(&s.partials, (size_t)s.n_sm * 64);
+            small.add(&s.log_tab, (size_t)kLogTab);
+            rc = small.commit(s);
+            if (rc) return rc;
+            CU(cudaMemsetAsync(s.slabs.back().first, 0, s.slabs.back().second, s.stream));
+        }
         CU(cudaMemsetAsync(s.col + s.nnz, 0, sizeof(int) * pad, s.stream));
         CU(cudaMemsetAsync(s.q + s.nnz, 0, sizeof(double) * pad, s.stream));
         if (tm.on) cudaStreamSynchronize(s.stream);
@@ -908,12 +955,19 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             CU(cudaStreamSynchronize(s.stream));
             if (flags & 1) return fail(TSC_ERR_ARG, "indptr is not non-decreasing");
             if (flags & 2) {            // empty reads: release this attempt's arrays and ask for the slow path
-                cleanup_tmp();
-                for (auto& sh : h->shards) {
+                for (auto& sh : h->shards) {        // release this attempt's slabs; streams and the transport stay
                     cudaSetDevice(sh.dev);
-                    void* ptrs[] = {sh.indptr, sh.col, sh.q, sh.wy, sh.bad, sh.tiles};
-                    for (void* p : ptrs) if (p) cudaFree(p);
+                    if (sh.stream) cudaStreamSynchronize(sh.stream);
+                    if (sh.tiles && !sh.in_slab(sh.tiles)) cudaFree(sh.tiles);
+                    for (auto& b : sh.slabs) cudaFree(b.first);
+                    sh.slabs.clear();
                     sh.indptr = nullptr; sh.col = nullptr; sh.q = nullptr; sh.wy = nullptr; sh.bad = nullptr; sh.tiles = nullptr;
+                    sh.raw = nullptr;
+                    double** kv[] = {&sh.pi, &sh.theta, &sh.pt, &sh.pi_prev, &sh.theta_prev, &sh.pt_prev, &sh.pi_init, &sh.theta_init,
+                                     &sh.pisum0, &sh.thetasum, &sh.ones, &sh.tmp_a, &sh.tmp_b, &sh.tmp_c, &sh.colsum, &sh.acc,
+                                     &sh.scalars, &sh.partials};
+                    for (double** p : kv) *p = nullptr;
+                    sh.perm = nullptr; sh.consts = nullptr; sh.st = nullptr; sh.log_tab = nullptr;
                 }
                 return kNeedsCompaction;
             }
@@ -994,33 +1048,21 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         }
     }
     tm.lap("locus classes");
-    const size_t kb = sizeof(double) * K;
     for (int i = 0; i < n_local; ++i) {
         Shard& s = h->shards[i];
         CU(cudaSetDevice(s.dev));
-        CU(cudaMalloc(&s.perm, sizeof(int) * K));
+        // (the K-sized arrays live in the shard's small slab, zeroed when it was allocated)
         CU(cudaMemcpyAsync(s.perm, h->perm.data(), sizeof(int) * K, cudaMemcpyHostToDevice, s.stream));
-        k_build_q<<<grid_for(s.nnz, 256, s.n_sm * 16), 256, 0, s.stream>>>(raw_d[i], colin_d[i], lut_d[i], lut_len, s.perm,
-                                                                        s.q, s.col, s.nnz, s.bad);
+        k_build_q<<<grid_for(s.nnz, 256, s.n_sm * 16), 256, 0, s.stream>>>(raw_d[i], colin_d[i], lut_d[i], lut_len,
+                                                                        permute ? s.perm : nullptr, s.q, s.col, s.nnz, s.bad);
         LAUNCH(h);
         CU(cudaGetLastError());
-        double** kv[] = {&s.pi, &s.theta, &s.pt, &s.pi_prev, &s.theta_prev, &s.pt_prev, &s.pi_init, &s.theta_init,
-                         &s.pisum0, &s.thetasum, &s.ones, &s.tmp_a, &s.tmp_b, &s.tmp_c, &s.colsum};
-        for (double** p : kv) { CU(cudaMalloc(p, kb)); CU(cudaMemsetAsync(*p, 0, kb, s.stream)); }
-        CU(cudaMalloc(&s.acc, kb * h->R));
-        CU(cudaMemsetAsync(s.acc, 0, kb * h->R, s.stream));
-        CU(cudaMalloc(&s.consts, sizeof(Consts)));
-        CU(cudaMalloc(&s.st, sizeof(EmState)));
-        CU(cudaMemsetAsync(s.st, 0, sizeof(EmState), s.stream));
-        CU(cudaMallocHost(&s.st_host, sizeof(EmState) * 2));
-        CU(cudaMalloc(&s.scalars, sizeof(double) * 8));
         CU(cudaMemsetAsync(s.scalars, 0, sizeof(double) * 8, s.stream));
+        CU(cudaMallocHost(&s.st_host, sizeof(EmState) * 2));
         CU(cudaEventCreateWithFlags(&s.ev_poll[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_poll[1], cudaEventDisableTiming));
         s.grid_rows = s.n_sm * 4;                   // 512-thread blocks, persistent grid-stride
         s.grid_tiles = s.n_sm * 2;                  // refined below from the occupancy of the tile kernel
-        CU(cudaMalloc(&s.partials, sizeof(double) * (s.n_sm * 64)));
-        CU(cudaMalloc(&s.log_tab, sizeof(LogTab) * kLogTab));
         k_log_table<<<1, kLogTab, 0, s.stream>>>(s.log_tab);
         LAUNCH(h);
         k_row_init<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(csr_of(s), s.wy, s.scalars, s.pisum0);
@@ -1043,12 +1085,9 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             CU(cudaSetDevice(s.dev));
             CU(cudaFuncSetAttribute(k_ell<ELL_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEllSmem));
             CU(cudaFuncSetAttribute(k_ell<ELL_LNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ell_smem_bytes<ELL_LNL>()));
-            Arena arena;
-            {   // the raw uploads are dead once Q is built: their memory serves the temporaries of the clustering
-                const int i = (int)(&s - &h->shards[0]);
-                CU(cudaStreamSynchronize(s.stream));
-                if (colin_d[i] && s.nnz > 0) { arena.base = (char*)colin_d[i]; arena.cap = sizeof(int) * (size_t)s.nnz; }
-            }
+            Arena arena;        // the raw scores are dead once Q is built: their memory serves the clustering's temporaries
+            CU(cudaStreamSynchronize(s.stream));
+            if (s.raw && s.nnz > 0) { arena.base = (char*)s.raw; arena.cap = sizeof(uint16_t) * (size_t)s.nnz; }
             int rc = build_ell(h, s, tm, &arena);
             if (rc) return rc;
         }

@@ -386,6 +386,8 @@ def main():
     c1 = tl.counters()
     kms = tl.kernel_times_ms()
     kern_ms = max_over_ranks(float(np.mean(kms)) if len(kms) else float("nan"))
+    tms = tl.tail_times_ms()
+    tail_ms = max_over_ranks(float(np.mean(tms)) if len(tms) else float("nan"))
     final_lnl = tl.lnl
 
     # other device passes of the path, timed alone (no host copies): standalone E-step (writes z), log-likelihood,
@@ -423,6 +425,7 @@ def main():
                           "calculate_lnl pass like the reference's em()",
                 "kernel": a.kernel, "transport": a.transport if world > 1 else "none (1 GPU)",
                 "wall_ms_per_step": wall * 1e3 / K, "gen_s": round(t_gen, 2),
+                "tail_ms_per_step": tail_ms, "tail": "replica sum + exchange between the GPUs + update + loop control (k_tail)",
             },
             "clocks": clocks,
             "e2e": {

@@ -142,6 +142,9 @@ int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_likelihood,
            double* diffs_out, double* lnls_out, int32_t* n_iter, int32_t* converged, double* final_lnl);
 /* per-iteration device time (ms, CUDA events) of the fused E+M kernel of the last tsc_em on local shard 0 */
 int tsc_get_kernel_times(tsc_handle* h, float* ms_out, int32_t max_n, int32_t* n_out);
+/* ... and of what follows it in the iteration: replica sum, exchange between the GPUs, parameter update, loop control
+ * (one kernel with the peer transport; reduce + ncclAllReduce + update with NCCL) */
+int tsc_get_tail_times(tsc_handle* h, float* ms_out, int32_t max_n, int32_t* n_out);
 /* device time (ms, CUDA events on the library's stream of local shard 0) of the whole last tsc_em loop, first
  * kernel to the final log-likelihood reduction */
 int tsc_get_em_device_ms(tsc_handle* h, float* ms_out);

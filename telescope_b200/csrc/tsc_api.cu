@@ -22,6 +22,7 @@
 #include <limits>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -128,7 +129,7 @@ struct Shard {
     int* bad = nullptr;
     ncclComm_t comm = nullptr;
     cudaEvent_t ev_poll[2] = {nullptr, nullptr};
-    std::vector<cudaEvent_t> ev_k;   // 2 per iteration, shard 0 only
+    std::vector<cudaEvent_t> ev_k;   // 3 per timed iteration, shard 0 only: before / after the fused kernels, after the tail
     cudaEvent_t ev_em[2] = {nullptr, nullptr};
     int n_sm = 0;
     int grid_rows = 0, grid_tiles = 0;
@@ -157,22 +158,29 @@ struct Shard {
     long long ell_bytes = 0, ell_slices = 0, ell_reads = 0, ell_entries = 0;
     int4* ell_index = nullptr;            // per slice record: offset / 16, first locus, T | last locus << 8, reads
     int ell_grid = 0, ell_grid_lnl = 0;
+    long long *ell_range = nullptr, *ell_range_lnl = nullptr;      // record boundaries of the CTAs (grid + 1 each)
     long long res_amb_rows = 0, res_amb_nnz = 0;   // the ambiguous part of the residual CSR (it also holds the unique reads)
     long long res_rows = 0, res_nnz = 0, res_n_tiles = 0, res_n_long = 0;
     long long* res_indptr = nullptr;
     int* res_col = nullptr;
     double* res_q = nullptr;
     double* res_wy = nullptr;
-    Tile* res_tiles = nullptr;
+    Tile* res_tiles = nullptr;            // over every read of the residual (log-likelihood)
+    Tile* res_tiles_amb = nullptr;        // over its ambiguous front only (fused E+M)
+    long long res_amb_tiles = 0, res_amb_long = 0;
 };
 
 struct tsc_handle {
     std::vector<Shard> shards;
     int K = 0, world = 1, n_procs = 1, proc_rank = 0;
-    int R = 8, G = 8, kernel = TSC_KERNEL_TILES;
+    int R = 8, G = 8, kernel = TSC_KERNEL_TILES;     // R: accumulator replicas allocated
+    int R_used = 8;                                  // ... and used (few when nearly everything goes through the stream)
     int transport = TSC_TRANSPORT_PEER;          // how the shards exchange K-vectors (TSC_TRANSPORT_*)
     int kpad = 0, nb_tail = 1, cap = 0;         // exchange-buffer geometry (tsc_peer.cuh)
     unsigned long long epoch_iter = 0, epoch_gen = 0;
+    std::thread peer_thread;                    // maps the other ranks' exchange buffers while the CSR is uploaded
+    int peer_thread_rc = TSC_OK;
+    std::string peer_thread_err;
     bool smem_tab = false;
     long long n_rows_user = 0, n_rows = 0, nnz = 0;
     std::vector<long long> rowmap;        // compacted read -> caller's read index (empty when no empty reads)
@@ -185,7 +193,7 @@ struct tsc_handle {
     bool em_done = false;
     int n_iter = 0, converged = 0;
     double lnl = std::numeric_limits<double>::infinity();
-    std::vector<float> kernel_ms;
+    std::vector<float> kernel_ms, tail_ms;
     float em_ms = 0.f;
     long long launches = 0, h2d = 0, d2h = 0;
 };
@@ -201,9 +209,17 @@ static PeerArgs peer_args(const tsc_handle* h, const Shard& s) {
     return PeerArgs{s.peer_ptrs_d, h->world, s.world_rank, h->kpad, h->nb_tail, h->cap};
 }
 
+// the other ranks' exchange buffers are mapped (the mapping thread of setup_transport has finished)
+static int peer_ready(tsc_handle* h) {
+    if (h->peer_thread.joinable()) h->peer_thread.join();
+    if (h->peer_thread_rc) return fail(h->peer_thread_rc, h->peer_thread_err);
+    return TSC_OK;
+}
+
 // In-place reduction of `count` 8-byte elements over every shard of every process.
 static int allreduce(tsc_handle* h, void* (*ptr_of)(Shard&), size_t count, ncclDataType_t dt, ncclRedOp_t op) {
     if (h->world == 1) return TSC_OK;
+    { int rc = peer_ready(h); if (rc) return rc; }
     if (h->transport == TSC_TRANSPORT_NCCL) {
         NC(g_nccl.GroupStart());
         for (auto& s : h->shards) {
@@ -279,20 +295,25 @@ static int launch_lnl_kernels(tsc_handle* h, Shard& s, const EmState* st, const 
                               const double* ia, const double* iu, int* nparts_out);
 
 // ------------------------------------------------------------------------------------------------- tile launches
+// CTAs of a tile pass: the resident grid, or fewer when the tile list is short (one tile per warp at least)
+static int tiles_grid(const Shard& s, long long n_tiles) {
+    return (int)std::max<long long>(1, std::min<long long>(s.grid_tiles, (n_tiles + kTileWarps - 1) / kTileWarps));
+}
+
 template <int MODE>
 static void launch_tiles(const Shard& s, const TileArgs& a, bool smem_tab, int long8_override = -1) {
     const size_t scratch = sizeof(double) * kTileWarps * kScratch;
     // > 0.5 % of the tiles are long reads (the residual CSR of the ELL path passes its own ratio)
     const bool long8 = long8_override >= 0 ? long8_override != 0 : s.n_long * 200 > s.n_tiles;
+    const int grid = tiles_grid(s, a.n_tiles);
     if (MODE == TILE_FUSED && smem_tab) {
-        if (long8) k_tiles<MODE, true, true><<<s.grid_tiles, kTileThreads, s.smem_tiles, s.stream>>>(a);
-        else k_tiles<MODE, true, false><<<s.grid_tiles, kTileThreads, s.smem_tiles, s.stream>>>(a);
+        if (long8) k_tiles<MODE, true, true><<<grid, kTileThreads, s.smem_tiles, s.stream>>>(a);
+        else k_tiles<MODE, true, false><<<grid, kTileThreads, s.smem_tiles, s.stream>>>(a);
     } else {
-        if (long8) k_tiles<MODE, false, true><<<s.grid_tiles, kTileThreads, scratch, s.stream>>>(a);
-        else k_tiles<MODE, false, false><<<s.grid_tiles, kTileThreads, scratch, s.stream>>>(a);
+        if (long8) k_tiles<MODE, false, true><<<grid, kTileThreads, scratch, s.stream>>>(a);
+        else k_tiles<MODE, false, false><<<grid, kTileThreads, scratch, s.stream>>>(a);
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------- small API
 extern "C" int tsc_abi_version(void) { return TSC_ABI_VERSION; }
@@ -342,7 +363,7 @@ static void free_shard(Shard& s) {
     void* ptrs[] = {s.indptr, s.col, s.q, s.wy, s.tiles, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
                     s.pi_init, s.theta_init, s.pisum0, s.acc, s.thetasum, s.ones, s.tmp_a, s.tmp_b, s.tmp_c, s.colsum,
                     s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad,
-                    s.ell_stream, s.ell_index, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles,
+                    s.ell_stream, s.ell_index, s.ell_range, s.ell_range_lnl, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles, s.res_tiles_amb,
                     s.peer_ptrs_d, s.tail_partials, s.tail_ticket, s.peer_err, s.log_tab};
     for (void* p : ptrs) if (p && !s.in_slab(p)) cudaFree(p);
     for (auto& b : s.slabs) cudaFree(b.first);
@@ -360,6 +381,7 @@ static void free_shard(Shard& s) {
 
 extern "C" void tsc_destroy(tsc_handle* h) {
     if (!h) return;
+    if (h->peer_thread.joinable()) h->peer_thread.join();
     for (auto& s : h->shards) free_shard(s);
     delete h;
 }
@@ -369,7 +391,7 @@ extern "C" void tsc_destroy(tsc_handle* h) {
 static void peer_geometry(int K, int* kpad, int* nb, int* cap) {
     *kpad = (K + 31) & ~31;
     *nb = (K + kTailBlockLoci - 1) / kTailBlockLoci;
-    *cap = 8 * *kpad + 64;
+    *cap = *kpad + 64;          // larger reductions go through the inbox in pieces
 }
 
 static int peer_buffer_alloc(int dev, int K, int world, unsigned char** out) {
@@ -451,20 +473,36 @@ static int setup_transport(tsc_handle* h, const tsc_config& cfg) {
             s.peer_map[s.world_rank] = s.peer_own;
         }
         if (h->n_procs > 1) {
-            Shard& s = h->shards[0];
-            CU(cudaSetDevice(s.dev));
-            for (int r = 0; r < h->world; ++r) {
-                if (r == s.world_rank) continue;
-                cudaIpcMemHandle_t hd;
-                memcpy(&hd, (const char*)cfg.peer_handles + 64 * (size_t)r, 64);
-                void* p = nullptr;
-                cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
-                if (e != cudaSuccess)
-                    return fail(TSC_ERR_CUDA, "cudaIpcOpenMemHandle(rank " + std::to_string(r) + "): " + cudaGetErrorString(e) +
-                                                  " -- the peer transport needs every GPU of the node visible to every rank");
-                s.peer_map[r] = (unsigned char*)p;
-                s.peer_opened[r] = 1;
+            // cudaIpcOpenMemHandle costs ~10 ms per peer: it runs beside the upload of the CSR; peer_ready() joins
+            {
+                Shard& s0 = h->shards[0];
+                CU(cudaSetDevice(s0.dev));
+                CU(cudaMalloc(&s0.peer_ptrs_d, sizeof(unsigned char*) * h->world));
             }
+            std::vector<char> handles((const char*)cfg.peer_handles, (const char*)cfg.peer_handles + 64 * (size_t)h->world);
+            h->peer_thread = std::thread([h, handles]() {
+                Shard& s = h->shards[0];
+                auto bad = [&](const std::string& what, cudaError_t e) {
+                    h->peer_thread_rc = TSC_ERR_CUDA;
+                    h->peer_thread_err = what + ": " + cudaGetErrorString(e);
+                };
+                cudaError_t e = cudaSetDevice(s.dev);
+                if (e != cudaSuccess) return bad("cudaSetDevice", e);
+                for (int r = 0; r < h->world; ++r) {
+                    if (r == s.world_rank) continue;
+                    cudaIpcMemHandle_t hd;
+                    memcpy(&hd, handles.data() + 64 * (size_t)r, 64);
+                    void* p = nullptr;
+                    e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+                    if (e != cudaSuccess)
+                        return bad("cudaIpcOpenMemHandle(rank " + std::to_string(r) + ") -- the peer transport needs every GPU of "
+                                   "the node visible to every rank", e);
+                    s.peer_map[r] = (unsigned char*)p;
+                    s.peer_opened[r] = 1;
+                }
+                e = cudaMemcpy(s.peer_ptrs_d, s.peer_map.data(), sizeof(unsigned char*) * h->world, cudaMemcpyHostToDevice);
+                if (e != cudaSuccess) return bad("peer pointer table", e);
+            });
         } else if (n_local > 1) {
             for (auto& a : h->shards) {
                 CU(cudaSetDevice(a.dev));
@@ -479,8 +517,10 @@ static int setup_transport(tsc_handle* h, const tsc_config& cfg) {
         }
         for (auto& s : h->shards) {
             CU(cudaSetDevice(s.dev));
-            CU(cudaMalloc(&s.peer_ptrs_d, sizeof(unsigned char*) * h->world));
-            CU(cudaMemcpy(s.peer_ptrs_d, s.peer_map.data(), sizeof(unsigned char*) * h->world, cudaMemcpyHostToDevice));
+            if (h->n_procs == 1) {
+                CU(cudaMalloc(&s.peer_ptrs_d, sizeof(unsigned char*) * h->world));
+                CU(cudaMemcpy(s.peer_ptrs_d, s.peer_map.data(), sizeof(unsigned char*) * h->world, cudaMemcpyHostToDevice));
+            }
             CU(cudaMalloc(&s.tail_partials, sizeof(double) * h->nb_tail));
             CU(cudaMalloc(&s.tail_ticket, sizeof(unsigned)));
             CU(cudaMemset(s.tail_ticket, 0, sizeof(unsigned)));
@@ -725,7 +765,6 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         int per_sm_lnl = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lnl, k_ell<ELL_LNL>, 32, ell_smem_bytes<ELL_LNL>()));
         const int warps = s.n_sm * std::max(per_sm, 1);
-        const long long n_seg = (n_slices + 31) / 32;      // a warp's unit of work between two window flushes
         lap("  ell slices+scan");
         if (total >= (1LL << 36)) return fail(TSC_ERR_ARG, "slice stream of one GPU exceeds 64 GB");
         CU(cudaMalloc(&s.ell_stream, (size_t)total));
@@ -736,8 +775,15 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         CU(cudaGetLastError());
         s.ell_bytes = total;
         s.ell_slices = n_slices;
-        s.ell_grid = (int)std::min<long long>(n_seg, warps);
-        s.ell_grid_lnl = (int)std::min<long long>(n_seg, (long long)s.n_sm * std::max(per_sm_lnl, 1));
+        // every resident warp gets a contiguous, byte-balanced run (at least ~8 records each when the stream is short)
+        s.ell_grid = (int)std::max<long long>(1, std::min<long long>((n_slices + 7) / 8, warps));
+        s.ell_grid_lnl = (int)std::max<long long>(1, std::min<long long>((n_slices + 7) / 8, (long long)s.n_sm * std::max(per_sm_lnl, 1)));
+        CU(cudaMalloc(&s.ell_range, sizeof(long long) * (s.ell_grid + 1)));
+        CU(cudaMalloc(&s.ell_range_lnl, sizeof(long long) * (s.ell_grid_lnl + 1)));
+        k_ell_ranges<<<(s.ell_grid + 256) / 256, 256, 0, s.stream>>>(rec_off, n_slices, s.ell_grid, s.ell_range);
+        k_ell_ranges<<<(s.ell_grid_lnl + 256) / 256, 256, 0, s.stream>>>(rec_off, n_slices, s.ell_grid_lnl, s.ell_range_lnl);
+        h->launches += 2;
+        CU(cudaGetLastError());
         lap("  ell fill");
     }
     // ---- residual CSR: every read without a slot in the stream -- the unique reads (they add nothing to the M-step
@@ -774,6 +820,10 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
             }
             CU(cudaMemsetAsync(s.res_col + s.res_nnz, 0, sizeof(int) * pad, s.stream));
             CU(cudaMemsetAsync(s.res_q + s.res_nnz, 0, sizeof(double) * pad, s.stream));
+            {   // counters[4]: cursor of the ambiguous front, counters[5]: cursor of the unique reads behind it
+                const unsigned long long start[2] = {0ULL, ((unsigned long long)s.res_amb_rows << kResShift) | (unsigned long long)s.res_amb_nnz};
+                CU(cudaMemcpyAsync(counters + 4, start, sizeof(start), cudaMemcpyHostToDevice, s.stream));
+            }
             k_res_append<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, key, counters + 4,
                                                                                      s.res_indptr, s.res_col, s.res_q, s.res_wy);
             LAUNCH(h);
@@ -781,6 +831,8 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
             CU(cudaGetLastError());
             CU(cudaStreamSynchronize(s.stream));
             int rc = build_tiles(h, s, s.res_indptr, s.res_rows, &s.res_tiles, &s.res_n_tiles, &s.res_n_long, arena);
+            if (!rc && s.res_amb_rows > 0)
+                rc = build_tiles(h, s, s.res_indptr, s.res_amb_rows, &s.res_tiles_amb, &s.res_amb_tiles, &s.res_amb_long, arena);
             if (rc) return rc;
             lap("  residual copy+tiles");
         }
@@ -883,6 +935,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
     tm.lap("streams + transport");
     // ---- tuning
     h->R = cfg.replicas > 0 ? std::min(cfg.replicas, 64) : 16;
+    h->R_used = h->R;
     const double avg = n_rows ? (double)nnz / (double)n_rows : 1.0;
     h->G = avg <= 5.0 ? 4 : avg <= 24.0 ? 8 : avg <= 64.0 ? 16 : 32;
     h->kernel = (cfg.kernel == TSC_KERNEL_ROWS || cfg.kernel == TSC_KERNEL_TILES) ? cfg.kernel : TSC_KERNEL_ELL;
@@ -1092,6 +1145,10 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             if (rc) return rc;
         }
         tm.lap("clustered ELL stream");
+        // the stream's flushes are a few thousand coalesced REDs per iteration: replicas only pay for the flat tiles
+        bool small_residual = cfg.replicas <= 0;
+        for (auto& s : h->shards) small_residual = small_residual && s.res_amb_nnz * 20 < std::max<long long>(s.nnz, 1);
+        if (small_residual) h->R_used = std::min(h->R, 2);
     }
     // totals over all shards (model.py:691-699)
     ALLREDUCE(h, s.scalars, 2, ncclFloat64, ncclSum);
@@ -1377,32 +1434,40 @@ extern "C" int tsc_get_kernel_times(tsc_handle* h, float* ms_out, int32_t max_n,
     return TSC_OK;
 }
 
+extern "C" int tsc_get_tail_times(tsc_handle* h, float* ms_out, int32_t max_n, int32_t* n_out) {
+    if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
+    const int n = (int)std::min<size_t>(h->tail_ms.size(), (size_t)std::max(max_n, 0));
+    if (ms_out) for (int i = 0; i < n; ++i) ms_out[i] = h->tail_ms[i];
+    if (n_out) *n_out = (int)h->tail_ms.size();
+    return TSC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------- EM
 static int launch_fused(tsc_handle* h, Shard& s, bool gated) {
     const EmState* st = gated ? s.st : nullptr;
     if (h->kernel == TSC_KERNEL_ROWS) {
         launch_rows(h->G, [&](auto g) {
-            k_fused_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), s.wy, s.pt, s.acc, h->K, h->R, st);
+            k_fused_rows<decltype(g)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), s.wy, s.pt, s.acc, h->K, h->R_used, st);
         });
         LAUNCH(h);
     } else if (h->kernel == TSC_KERNEL_ELL) {
         // the clustered stream, then whatever does not fit a slice through the flat tiles of the residual CSR
         if (s.ell_slices > 0) {
-            EllArgs e{s.ell_stream, s.ell_index, s.ell_slices, s.pt, s.acc, h->K, h->R, st, nullptr, nullptr, nullptr};
+            EllArgs e{s.ell_stream, s.ell_index, s.ell_range, s.ell_slices, s.pt, s.acc, h->K, h->R_used, st, nullptr, nullptr, nullptr};
             k_ell<ELL_FUSED><<<s.ell_grid, 32, kEllSmem, s.stream>>>(e);
             LAUNCH(h);
         }
         if (s.res_amb_rows > 0) {         // (a residual of unique reads only has nothing to add)
             TileArgs a{};
-            a.tiles = s.res_tiles; a.n_tiles = s.res_n_tiles; a.q = s.res_q; a.col = s.res_col; a.wy = s.res_wy; a.tab_amb = s.pt;
-            a.acc = s.acc; a.K = h->K; a.R = h->R; a.s_cols = 0; a.st = st;
-            launch_tiles<TILE_FUSED>(s, a, false, s.res_n_long * 200 > s.res_n_tiles ? 1 : 0);
+            a.tiles = s.res_tiles_amb; a.n_tiles = s.res_amb_tiles; a.q = s.res_q; a.col = s.res_col; a.wy = s.res_wy; a.tab_amb = s.pt;
+            a.acc = s.acc; a.K = h->K; a.R = h->R_used; a.s_cols = 0; a.st = st;
+            launch_tiles<TILE_FUSED>(s, a, false, s.res_amb_long * 200 > s.res_amb_tiles ? 1 : 0);
             LAUNCH(h);
         }
     } else {
         TileArgs a{};
         a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.wy = s.wy; a.tab_amb = s.pt;
-        a.acc = s.acc; a.K = h->K; a.R = h->R; a.s_cols = s.s_cols; a.st = st;
+        a.acc = s.acc; a.K = h->K; a.R = h->R_used; a.s_cols = s.s_cols; a.st = st;
         launch_tiles<TILE_FUSED>(s, a, s.s_cols > 0);
         LAUNCH(h);
     }
@@ -1421,7 +1486,7 @@ static int launch_lnl_kernels(tsc_handle* h, Shard& s, const EmState* st, const 
     a.tab_amb = ta; a.tab_uni = tu; a.inner_amb = ia; a.inner_uni = iu; a.K = h->K; a.st = st; a.log_tab = s.log_tab;
     if (h->kernel == TSC_KERNEL_ELL) {
         if (s.ell_slices > 0) {
-            EllArgs e{s.ell_stream, s.ell_index, s.ell_slices, ta, nullptr, h->K, 1, st, ia, s.partials, s.log_tab};
+            EllArgs e{s.ell_stream, s.ell_index, s.ell_range_lnl, s.ell_slices, ta, nullptr, h->K, 1, st, ia, s.partials, s.log_tab};
             k_ell<ELL_LNL><<<s.ell_grid_lnl, 32, ell_smem_bytes<ELL_LNL>(), s.stream>>>(e);
             LAUNCH(h);
             nparts = s.ell_grid_lnl;
@@ -1430,13 +1495,13 @@ static int launch_lnl_kernels(tsc_handle* h, Shard& s, const EmState* st, const 
             a.tiles = s.res_tiles; a.n_tiles = s.res_n_tiles; a.q = s.res_q; a.col = s.res_col; a.partials = s.partials + nparts;
             launch_tiles<TILE_LNL>(s, a, false, s.res_n_long * 200 > s.res_n_tiles ? 1 : 0);
             LAUNCH(h);
-            nparts += s.grid_tiles;
+            nparts += tiles_grid(s, a.n_tiles);
         }
     } else {
         a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.partials = s.partials;
         launch_tiles<TILE_LNL>(s, a, false);
         LAUNCH(h);
-        nparts = s.grid_tiles;
+        nparts = tiles_grid(s, a.n_tiles);
     }
     CU(cudaGetLastError());
     *nparts_out = nparts;
@@ -1475,6 +1540,7 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
                       double* lnls_out, int32_t* n_iter, int32_t* converged, double* final_lnl) {
     if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
     if (use_likelihood && !lnls_out) return fail(TSC_ERR_ARG, "lnls_out required with use_likelihood");
+    { int rc = peer_ready(h); if (rc) return rc; }
     const int T = std::max(1, (int)max_iter);   // the reference's loop body always runs once (model.py:771-794)
     const int K = h->K;
     for (auto& s : h->shards) {
@@ -1498,7 +1564,7 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
     // kernel-time events: a bounded pool (the first kTimedIters iterations of a call are timed), created on demand
     constexpr int kTimedIters = 512;
     const int n_timed = std::min(T, kTimedIters);
-    while ((int)s0.ev_k.size() < 2 * n_timed) {
+    while ((int)s0.ev_k.size() < 3 * n_timed) {
         cudaEvent_t e;
         CU(cudaEventCreate(&e));
         s0.ev_k.push_back(e);
@@ -1511,12 +1577,12 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
     for (int it = 0; it < T && !stop; ++it) {
         for (auto& s : h->shards) {
             CU(cudaSetDevice(s.dev));
-            if (&s == &s0 && it < n_timed) CU(cudaEventRecord(s0.ev_k[2 * it], s.stream));
+            if (&s == &s0 && it < n_timed) CU(cudaEventRecord(s0.ev_k[3 * it], s.stream));
             int rc = launch_fused(h, s, true);
             if (rc) return rc;
-            if (&s == &s0 && it < n_timed) CU(cudaEventRecord(s0.ev_k[2 * it + 1], s.stream));
+            if (&s == &s0 && it < n_timed) CU(cudaEventRecord(s0.ev_k[3 * it + 1], s.stream));
             if (h->transport == TSC_TRANSPORT_NCCL) {
-                k_reduce_replicas<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.acc, K, h->R, s.thetasum, s.st);
+                k_reduce_replicas<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.acc, K, h->R_used, s.thetasum, s.st);
                 LAUNCH(h);
                 CU(cudaGetLastError());
             }
@@ -1537,12 +1603,13 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
                 CU(cudaSetDevice(s.dev));
                 TailArgs a{UpdateArgs{nullptr, s.pisum0, s.consts, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
                                       s.pi_init, s.theta_init, s.st, s.diffs, K, T, use_likelihood ? 1 : 0, eps, s.rep},
-                           peer_args(h, s), s.acc, h->R, h->epoch_iter, s.tail_partials, s.tail_ticket};
+                           peer_args(h, s), s.acc, h->R_used, h->epoch_iter, s.tail_partials, s.tail_ticket};
                 k_tail<<<h->nb_tail, kTailThreads, 0, s.stream>>>(a);
                 LAUNCH(h);
                 CU(cudaGetLastError());
             }
         }
+        if (it < n_timed) { CU(cudaSetDevice(s0.dev)); CU(cudaEventRecord(s0.ev_k[3 * it + 2], s0.stream)); }
         if (use_likelihood) {
             int rc = launch_lnl(h, nullptr, true, true,
                                 [](Shard& s) -> const double* { return s.pt; }, [](Shard& s) -> const double* { return s.pi; });
@@ -1578,10 +1645,13 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
     h->converged = fin.converged;
     h->em_done = true;
     h->kernel_ms.clear();
+    h->tail_ms.clear();
     for (int it = 0; it < std::min(std::min(issued, fin.iter), n_timed); ++it) {
         float ms = 0;
-        CU(cudaEventElapsedTime(&ms, s0.ev_k[2 * it], s0.ev_k[2 * it + 1]));
+        CU(cudaEventElapsedTime(&ms, s0.ev_k[3 * it], s0.ev_k[3 * it + 1]));
         h->kernel_ms.push_back(ms);
+        CU(cudaEventElapsedTime(&ms, s0.ev_k[3 * it + 1], s0.ev_k[3 * it + 2]));
+        h->tail_ms.push_back(ms);
     }
     if (use_likelihood) {
         h->lnl = fin.lnl;

@@ -14,7 +14,8 @@
 //     atomics at all in the loop.  A window block is flushed (16 copies summed in fixed order, one coalesced
 //     RED.ADD.F64 of 32 doubles) only when the sorted stream has moved past it: a few thousand sector REDs per
 //     iteration instead of 5e8.
-// The slice records form one byte stream in HBM; a warp takes segments of 32 consecutive records.  It asks the TMA
+// The slice records form one byte stream in HBM; every warp takes one contiguous, byte-balanced run of it (batches of
+// 32 records: one index load per lane).  It asks the TMA
 // unit to pull each record into L2 several records ahead (cp.async.bulk.prefetch.L2, one instruction per record) and
 // then loads the record's loci / Q straight into registers -- every load of a slice is in flight at once, all of them
 // L2 hits.  (A first version staged the records in a shared-memory ring with cp.async.bulk + mbarrier; ncu showed the
@@ -193,6 +194,18 @@ __global__ void k_ell_slices(const long long* __restrict__ ip, const int* __rest
     }
 }
 
+// Work split of the stream kernels: CTA w takes the records that START in [w, w+1) * total / n_ctas bytes -- one
+// contiguous, byte-balanced run of the sorted stream per warp.  range[w] = first record of CTA w, range[n_ctas] = n.
+__global__ void k_ell_ranges(const long long* __restrict__ rec_off, long long n_slices, int n_ctas, long long* __restrict__ range) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > n_ctas) return;
+    const long long total = rec_off[n_slices];
+    const long long target = (w == n_ctas) ? total : (long long)((__int128)total * w / n_ctas);
+    long long lo = 0, hi = n_slices;          // first record with rec_off >= target
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (rec_off[mid] < target) lo = mid + 1; else hi = mid; }
+    range[w] = lo;
+}
+
 // One warp per slice writes its record and completes its index entry.
 __global__ void __launch_bounds__(256) k_ell_fill(const long long* __restrict__ ip, const int* __restrict__ col,
                                                   const double* __restrict__ q, const double* __restrict__ wy,
@@ -262,7 +275,8 @@ __global__ void k_res_count(const long long* __restrict__ ip, long long n_rows, 
 }
 
 // 8 lanes per read; a residual read takes its place (read slot, first entry) from one packed atomic, so the read
-// pointers come out increasing in slot order whatever order the reads arrive in.
+// pointers come out increasing in slot order whatever order the reads arrive in.  Ambiguous reads fill the front of
+// the residual (the fused kernel only visits those), unique reads the rest: cursor[1] starts where the front ends.
 __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ col,
                                                     const double* __restrict__ q, const double* __restrict__ wy,
                                                     const int* __restrict__ key, unsigned long long* __restrict__ cursor,
@@ -277,8 +291,8 @@ __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict_
         long long b = 0, e = 0;
         bool res = false;
         if (r < n_rows) { b = ip[r]; e = ip[r + 1]; res = (key == nullptr || key[r] < 0); }
-        unsigned long long old = 0;
-        if (res && lane == 0) old = atomicAdd(cursor, (1ULL << kResShift) | (unsigned long long)(e - b));
+        unsigned long long old = 0;     // cursor[0]: ambiguous reads (the front of the residual), cursor[1]: unique reads
+        if (res && lane == 0) old = atomicAdd(cursor + ((e - b >= 2) ? 0 : 1), (1ULL << kResShift) | (unsigned long long)(e - b));
         old = __shfl_sync(gmask, old, (threadIdx.x & 31) & ~7);
         if (!res) continue;
         const long long rp = (long long)(old >> kResShift), o = (long long)(old & ((1ULL << kResShift) - 1ULL));
@@ -299,6 +313,7 @@ enum { ELL_FUSED = 0, ELL_LNL = 1 };
 struct EllArgs {
     const unsigned char* stream;
     const int4* index;            // per record: byte offset / 16, lo, T | hi << 8, reads
+    const long long* range;       // gridDim.x + 1 record boundaries: CTA w takes records [range[w], range[w+1])
     long long n_slices;
     const double* pt;             // pi*theta of the E-step (every read of the stream is ambiguous)
     double* acc;                  // FUSED: R replicas of K doubles
@@ -415,9 +430,7 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
     double* s_in = s_pt + kEllWin + 8;
     LogTab* s_log = reinterpret_cast<LogTab*>(s_in + kEllWin + 8);
     const int lane = threadIdx.x;
-    const int nw = gridDim.x;
-    const long long n_slices = a.n_slices;
-    const int n_seg = (int)((n_slices + 31) >> 5);            // a segment = 32 consecutive records
+    const long long r_begin = a.range[blockIdx.x], r_end = a.range[blockIdx.x + 1];     // this warp's run of records
     const int K = a.K;
     const double* __restrict__ pt = a.pt;
     const unsigned char* __restrict__ stream = a.stream;
@@ -432,13 +445,10 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
     }
     __syncwarp();
 
-    // lane l of a segment's index registers describes record 32*seg + l (T = 0 beyond the end)
-    auto load_seg = [&](int seg) -> int4 {
+    // lane l of a batch's index registers describes record b + l (T = 0 beyond the end of the run)
+    auto load_batch = [&](long long b) -> int4 {
         int4 v = make_int4(0, 0, 0, 0);
-        if (seg < n_seg) {
-            const long long idx = ((long long)seg << 5) + lane;
-            if (idx < n_slices) v = __ldg(a.index + idx);
-        }
+        if (b + lane < r_end) v = __ldg(a.index + b + lane);
         return v;
     };
     auto prefetch_mine = [&](const int4& v) {          // this lane's record -> L2
@@ -456,15 +466,15 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
         if (j < K && s != 0.0) atomicAdd(my + j, s);
     };
 
-    int4 cur = load_seg(blockIdx.x), nxt = load_seg(blockIdx.x + nw);
-    if (lane < kEllAhead) prefetch_mine(cur);         // the first records of the first segment
+    int4 cur = load_batch(r_begin), nxt = load_batch(r_begin + 32);
+    if (lane < kEllAhead) prefetch_mine(cur);         // the first records of the run
     int Fb = -1;                                      // first block (32 loci) of the window; -1 = empty
 
-    for (int seg = blockIdx.x; seg < n_seg; seg += nw) {
-        const int4 after = load_seg(seg + 2 * nw);    // requested two segments early
-        const int nrec = (int)min(32LL, n_slices - ((long long)seg << 5));
+    for (long long b = r_begin; b < r_end; b += 32) {
+        const int4 after = load_batch(b + 64);        // requested two batches early
+        const int nrec = (int)min(32LL, r_end - b);
         for (int c = 0; c < nrec; ++c) {
-            // ---- the lane that owns record c + kEllAhead (of this segment or the next) sends it to L2
+            // ---- the lane that owns record c + kEllAhead (of this batch or the next) sends it to L2
             {
                 const int pc = c + kEllAhead;
                 if (lane == (pc & 31)) prefetch_mine(pc < 32 ? cur : nxt);
@@ -483,14 +493,14 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
                 if (Fb >= 0) {
                     if (MODE == ELL_FUSED) {
                         const int e = min(lb, Fb + 4);
-                        for (int b = Fb; b < e; ++b) flush_block(b);
+                        for (int blk = Fb; blk < e; ++blk) flush_block(blk);
                     }
                     first_new = max(lb, Fb + 4);
                 }
-                for (int b = first_new; b < lb + 4; ++b) {
-                    const int j = b * 32 + lane;
-                    s_pt[(b & 3) * 32 + lane] = (j < K) ? __ldg(pt + j) : 0.0;
-                    if (MODE == ELL_LNL) s_in[(b & 3) * 32 + lane] = (j < K) ? __ldg(a.inner + j) : 0.0;
+                for (int blk = first_new; blk < lb + 4; ++blk) {
+                    const int j = blk * 32 + lane;
+                    s_pt[(blk & 3) * 32 + lane] = (j < K) ? __ldg(pt + j) : 0.0;
+                    if (MODE == ELL_LNL) s_in[(blk & 3) * 32 + lane] = (j < K) ? __ldg(a.inner + j) : 0.0;
                 }
                 Fb = lb;
                 __syncwarp();
@@ -506,12 +516,11 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
         }
         cur = nxt;
         nxt = after;
-        if (MODE == ELL_FUSED) {
-            // ---- segment done: hand the window to the global accumulator
-            __syncwarp();
-            if (Fb >= 0) for (int b = Fb; b < Fb + 4; ++b) flush_block(b);
-            Fb = -1;
-        }
+    }
+    if (MODE == ELL_FUSED) {
+        // ---- run done: hand the window to the global accumulator
+        __syncwarp();
+        if (Fb >= 0) for (int blk = Fb; blk < Fb + 4; ++blk) flush_block(blk);
     }
     if (MODE == ELL_LNL) {
         lnl_local = group_sum<32>(lnl_local, 0xffffffffu);

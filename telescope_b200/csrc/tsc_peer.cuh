@@ -29,6 +29,7 @@ namespace tsc {
 
 constexpr int kTailThreads = 256;
 constexpr int kTailLoci = 4;                              // loci per thread
+static_assert(kTailLoci == 4, "k_tail initialises four sums");
 constexpr int kTailBlockLoci = kTailThreads * kTailLoci;  // 1024 loci per block
 
 struct PeerArgs {
@@ -101,13 +102,17 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const TailArgs a) {
     const int parity = (int)(epoch & 1ULL);
     unsigned char* own = a.p.bufs[a.p.rank];
     // ---- 1 + 2: this GPU's sums of the block's loci, pushed to every rank
-    double s[kTailLoci];
+    double s[kTailLoci] = {0.0, 0.0, 0.0, 0.0};
+    {   // all loads of a replica row are independent: keep 4 loci x 4 replicas in flight per thread
+        const int j0 = blockIdx.x * kTailBlockLoci + tid;
+#pragma unroll 4
+        for (int r = 0; r < a.R; ++r) {
+            double* row = a.acc + (size_t)r * K;
 #pragma unroll
-    for (int i = 0; i < kTailLoci; ++i) {
-        const int j = blockIdx.x * kTailBlockLoci + i * kTailThreads + tid;
-        s[i] = 0.0;
-        if (j < K) {
-            for (int r = 0; r < a.R; ++r) { s[i] += a.acc[(size_t)r * K + j]; a.acc[(size_t)r * K + j] = 0.0; }
+            for (int i = 0; i < kTailLoci; ++i) {
+                const int j = j0 + i * kTailThreads;
+                if (j < K) { s[i] += row[j]; row[j] = 0.0; }
+            }
         }
     }
     for (int q = 0; q < a.p.world; ++q) {

@@ -307,6 +307,13 @@ class TelescopeLikelihood(object):
         _abi.check(self._lib.tsc_get_kernel_times(self._h, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size, C.byref(n)))
         return buf[:min(n.value, buf.size)]
 
+    def tail_times_ms(self):
+        """Per-iteration device time of the iteration's tail (exchange between GPUs + update + loop control)."""
+        n = C.c_int32(0)
+        buf = np.zeros(max(1, self.n_iter), dtype=np.float32)
+        _abi.check(self._lib.tsc_get_tail_times(self._h, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size, C.byref(n)))
+        return buf[:min(n.value, buf.size)]
+
     def em_device_ms(self):
         ms = C.c_float(0)
         _abi.check(self._lib.tsc_get_em_device_ms(self._h, C.byref(ms)))

@@ -63,18 +63,28 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 // spin until *flag >= epoch; false after ~20 s (a peer died): the caller records the error instead of hanging the GPU
+template <bool GPU_SCOPE>
 __device__ __forceinline__ bool peer_wait(const unsigned long long* flag, unsigned long long epoch) {
-    if (ld_acquire_sys(flag) >= epoch) return true;
+    auto poll = [&]() { return GPU_SCOPE ? ld_acquire_gpu(flag) : ld_acquire_sys(flag); };
+    if (poll() >= epoch) return true;
     const unsigned long long t0 = globaltimer_ns();
     for (;;) {
         for (int i = 0; i < 64; ++i)
-            if (ld_acquire_sys(flag) >= epoch) return true;
+            if (poll() >= epoch) return true;
         if (globaltimer_ns() - t0 > 20000000000ULL) return false;
         __nanosleep(200);
     }
@@ -123,14 +133,20 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const TailArgs a) {
             if (j < K) in[j] = s[i];
         }
     }
-    __threadfence_system();
+    // the block's stores happen-before the barrier, the flag's release (cumulative) publishes them: system scope when
+    // other GPUs read them, device scope (several microseconds cheaper) when the model lives on one GPU
     __syncthreads();
-    if (tid < a.p.world) st_release_sys(peer_flags_iter(a.p.bufs[tid]) + (size_t)a.p.rank * a.p.nb_max + blockIdx.x, epoch);
+    const bool solo = a.p.world == 1;
+    if (tid < a.p.world) {
+        unsigned long long* f = peer_flags_iter(a.p.bufs[tid]) + (size_t)a.p.rank * a.p.nb_max + blockIdx.x;
+        if (solo) st_release_gpu(f, epoch); else st_release_sys(f, epoch);
+    }
     // ---- 3: every rank's every block has delivered (identical loci of another block may be needed: `rep`)
     bool ok = true;
     for (int f = tid; f < a.p.world * (int)gridDim.x; f += kTailThreads) {
         const int r = f / (int)gridDim.x, b = f - r * (int)gridDim.x;
-        ok = peer_wait(peer_flags_iter(own) + (size_t)r * a.p.nb_max + b, epoch) && ok;
+        const unsigned long long* fl = peer_flags_iter(own) + (size_t)r * a.p.nb_max + b;
+        ok = (solo ? peer_wait<true>(fl, epoch) : peer_wait<false>(fl, epoch)) && ok;
     }
     if (!ok) st->pad = 1;                      // error flag, read by the host after the loop
     __syncthreads();
@@ -191,10 +207,9 @@ __global__ void __launch_bounds__(1024) k_peer_allreduce(const PeerArgs p, unsig
         unsigned long long* in = peer_inbox_gen(p, p.bufs[q], parity, p.rank);
         for (int i = tid; i < n; i += 1024) in[i] = data[i];
     }
-    __threadfence_system();
     __syncthreads();
     if (tid < p.world) st_release_sys(peer_flags_gen(p, p.bufs[tid]) + p.rank, epoch);
-    if (tid < p.world && !peer_wait(peer_flags_gen(p, own) + tid, epoch)) *err = 1;
+    if (tid < p.world && !peer_wait<false>(peer_flags_gen(p, own) + tid, epoch)) *err = 1;
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
         unsigned long long acc = __ldcg(peer_inbox_gen(p, own, parity, 0) + i);

@@ -974,7 +974,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             for (double** p : kv) small.add(p, kk);
             small.add(&s.acc, kk * h->R);
             small.add(&s.perm, kk);
-            small.add(&cnt_d[i], kk * 4);
+            small.add(&cnt_d[i], kk * 5);
             small.add(&lut_d[i], (size_t)lut_len);
             small.add(&s.bad, 1);
             small.add(&s.consts, 1);
@@ -1048,7 +1048,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
     {   // global per-locus entry counts -> internal numbering (descending count, ties by original index)
         static_assert(sizeof(unsigned long long) == 8, "");
         for (int i = 0; i < n_local; ++i) h->shards[i].xchg_ptr = cnt_d[i];
-        ALLREDUCE(h, s.xchg_ptr, (size_t)K * 4, ncclUint64, ncclSum);
+        ALLREDUCE(h, s.xchg_ptr, (size_t)K * 5, ncclUint64, ncclSum);
         for (auto& s : h->shards) {
             int bad = 0;
             CU(cudaSetDevice(s.dev));
@@ -1056,13 +1056,13 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             CU(cudaStreamSynchronize(s.stream));
             if (bad) return fail(TSC_ERR_ARG, "column index out of range [0, n_cols)");
         }
-        std::vector<unsigned long long> cnt((size_t)K * 4);
+        std::vector<unsigned long long> cnt((size_t)K * 5);
         Shard& s0 = h->shards[0];
         CU(cudaSetDevice(s0.dev));
-        CU(cudaMemcpyAsync(cnt.data(), cnt_d[0], sizeof(unsigned long long) * K * 4, cudaMemcpyDeviceToHost, s0.stream));
+        CU(cudaMemcpyAsync(cnt.data(), cnt_d[0], sizeof(unsigned long long) * K * 5, cudaMemcpyDeviceToHost, s0.stream));
         CU(cudaStreamSynchronize(s0.stream));
-        h->d2h += sizeof(unsigned long long) * K * 4;
-        h->pos_count.assign(cnt.begin() + 3 * (size_t)K, cnt.end());      // entries with a positive score, per locus
+        h->d2h += sizeof(unsigned long long) * K * 5;
+        h->pos_count.assign(cnt.begin() + 3 * (size_t)K, cnt.begin() + 4 * (size_t)K);      // entries with a positive score, per locus
         h->inv.resize(K);
         std::iota(h->inv.begin(), h->inv.end(), 0);
         if (cfg.permute_columns)
@@ -1072,14 +1072,17 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         // classes of identical columns (same count and both signatures); empty loci are trivially identical too
         std::vector<int> order(K);
         std::iota(order.begin(), order.end(), 0);
+        // a class = loci that agree in both exact counts and all three 64-bit signatures
         auto key_less = [&](int a, int b) {
-            if (cnt[a] != cnt[b]) return cnt[a] < cnt[b];
-            if (cnt[K + a] != cnt[K + b]) return cnt[K + a] < cnt[K + b];
-            if (cnt[2 * (size_t)K + a] != cnt[2 * (size_t)K + b]) return cnt[2 * (size_t)K + a] < cnt[2 * (size_t)K + b];
+            for (int w = 0; w < 5; ++w) {
+                const unsigned long long x = cnt[(size_t)w * K + a], y = cnt[(size_t)w * K + b];
+                if (x != y) return x < y;
+            }
             return a < b;
         };
         auto key_eq = [&](int a, int b) {
-            return cnt[a] == cnt[b] && cnt[K + a] == cnt[K + b] && cnt[2 * (size_t)K + a] == cnt[2 * (size_t)K + b];
+            for (int w = 0; w < 5; ++w) if (cnt[(size_t)w * K + a] != cnt[(size_t)w * K + b]) return false;
+            return true;
         };
         std::sort(order.begin(), order.end(), key_less);
         std::vector<int> rep_internal(K);

@@ -25,8 +25,9 @@
 //
 // Record (16-byte aligned, 128 + 288*T bytes):  double wy[16] | uint8 wcol[T][32] | double q[T][32]
 // Index (16 bytes per record): byte offset / 16, first locus lo, T | last locus << 8.
-// wcol = locus & 127, the entry's row in the window (blocks of 32 loci live in slot (locus >> 5) & 3), or 128 for an
-// empty slot: the dummy row, with q = 0 and pi*theta = 0, so empty slots add an exact +0.0 to a word nobody reads.
+// wcol = locus & 127, the entry's row in the window (blocks of 32 loci live in slot (locus >> 5) & 3), or 128 + (lane >> 4)
+// for an empty slot: a dummy row per half-warp (every lane has its own dummy word), with q = 0 and pi*theta = 0, so
+// empty slots add an exact +0.0 to a word nobody reads.
 // With one byte per locus the stream moves ~9.5 B per entry where canonical CSR moves 12.
 //
 // Reads that do not fit a slice (fewer than 2 or more than 2*kEllTMax entries, a locus span above kEllSpan, or
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(256) k_ell_fill(const long long* __restrict__ 
         for (int t = 0; t < T; ++t) {
             const int k = 2 * t + h;
             double qv = 0.0;
-            int d = kEllWin;                                          // empty slot: the dummy row
+            int d = kEllWin + h;                                      // empty slot: this half-warp's dummy row
             if (k < len) { qv = q[b + k]; d = col[b + k] & (kEllWin - 1); }
             dc[t * 32 + lane] = (unsigned char)d;
             qq[t * 32 + lane] = qv;
@@ -326,7 +327,7 @@ struct EllArgs {
 
 template <int MODE>
 __host__ __device__ constexpr size_t ell_smem_bytes() {
-    return MODE == ELL_FUSED ? sizeof(double) * ((kEllWin + 1) * kEllReads + kEllWin + 8)
+    return MODE == ELL_FUSED ? sizeof(double) * ((kEllWin + 2) * kEllReads + kEllWin + 8)
                              : sizeof(double) * 2 * (kEllWin + 8) + sizeof(LogTab) * kLogTab;
 }
 constexpr size_t kEllSmem = ell_smem_bytes<ELL_FUSED>();
@@ -371,7 +372,7 @@ __device__ __forceinline__ void ell_body(const unsigned char* __restrict__ rec, 
 #pragma unroll
     for (int t = 0; t < TM; ++t) {
         n[t] = 0.0;
-        ao[t] = kEllWin;                              // dummy row
+        ao[t] = kEllWin + (lane >> 4);                // this half-warp's dummy row
         if (t < TM - 3 || t < T) {
             ao[t] = __ldg(cp + 32 * t);
             n[t] = ell_ld_stream(qp + 32 * t);
@@ -423,10 +424,10 @@ template <int MODE>
 __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     if (a.st && a.st->done) return;
-    // FUSED: s_acc [kEllWin + 1][kEllReads] (last row = dummy) | s_pt [kEllWin + 8] ([kEllWin] = 0 for empty slots)
+    // FUSED: s_acc [kEllWin + 2][kEllReads] (last two rows = dummies) | s_pt [kEllWin + 8] ([kEllWin..] = 0 for empty slots)
     // LNL:   s_pt [kEllWin + 8] | s_in [kEllWin + 8] | log table
     double* s_acc = reinterpret_cast<double*>(s_raw);
-    double* s_pt = (MODE == ELL_FUSED) ? s_acc + (kEllWin + 1) * kEllReads : s_acc;
+    double* s_pt = (MODE == ELL_FUSED) ? s_acc + (kEllWin + 2) * kEllReads : s_acc;
     double* s_in = s_pt + kEllWin + 8;
     LogTab* s_log = reinterpret_cast<LogTab*>(s_in + kEllWin + 8);
     const int lane = threadIdx.x;

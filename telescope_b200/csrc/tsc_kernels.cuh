@@ -162,12 +162,13 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {   //
     return x;
 }
 
-// Per-locus entry count and an order-independent signature of the locus's column {(read, score)}: two 64-bit sums of
-// independent hashes.  Loci with equal (count, sig1, sig2) hold identical columns; the reference gives such loci
-// bit-identical pi/theta (its column sums run in read order), which reassign()'s exact tie test depends on.
+// Per-locus entry count and an order-independent signature of the locus's column {(read, score)}: three 64-bit sums
+// of independently mixed hashes, plus the number of positive scores.  Loci that agree in all five words (2 exact
+// counts + 192 hash bits) are taken to hold identical columns; the reference gives such loci bit-identical pi/theta
+// (its column sums run in read order), which reassign()'s exact tie test depends on.
 __global__ void k_col_signature(const long long* __restrict__ indptr, long long n_rows, const int* __restrict__ col,
                                 const uint16_t* __restrict__ raw, int n_cols, unsigned long long row_key0,
-                                unsigned long long* __restrict__ sig /* 4*K: count, sum h1, sum h2, count of scores > 0 */,
+                                unsigned long long* __restrict__ sig /* 5*K: count, sum h1, sum h2, count of scores > 0, sum h3 */,
                                 int* __restrict__ bad) {
     long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -181,6 +182,7 @@ __global__ void k_col_signature(const long long* __restrict__ indptr, long long 
             atomicAdd(sig + n_cols + c, mix64(e));
             atomicAdd(sig + 2 * (size_t)n_cols + c, mix64(e ^ 0xd6e8feb86659fd93ULL));
             if (raw[k] != 0) atomicAdd(sig + 3 * (size_t)n_cols + c, 1ULL);
+            atomicAdd(sig + 4 * (size_t)n_cols + c, mix64((e + 0x2545f4914f6cdd1dULL) * 0xff51afd7ed558ccdULL));
         }
     }
 }

@@ -106,6 +106,58 @@ def test_cli_assign_and_resume_reproduce_reference_reports(tmp_path):
     assert _strip_version(open(os.path.join(out2, "again-run_stats.tsv")).read()) == _strip_version(open(os.path.join(GOLD, "bundled_run_stats.tsv")).read())
 
 
+def test_updated_sam_records_follow_the_reference_rules(tmp_path):
+    """`--updated_sam` after a GPU EM run, record by record.  pysam is not in this image, so the reference's
+    `update_sam` (model.py:479-521) cannot write a golden BAM; its rules are restated here over the parsed records
+    and applied to the ORACLE's posterior and `exclude` assignment (bit-identical to the reference class on the
+    bundled data, tests/test_oracle.py):
+      ZT == SEC                      -> secondary flag, YC 248,248,248, MAPQ 0                       (model.py:501-504)
+      otherwise XP = round(100 z), MAPQ = phred(z) = round(-10 log10(1 - z)) or 255 at z = 1        (model.py:506-509, helpers.py:14-37)
+        assigned (mat > 0)           -> secondary flag cleared, YC 217,95,2 (vermilion)              (model.py:510-512)
+        not assigned                 -> secondary flag, YC 230,171,2 if z >= 0.2 else 209,236,228   (model.py:513-518)"""
+    from oracle.em_numpy import EMOracle
+    from telescope_b200 import cli
+    from telescope_b200.host import bam
+    data = os.path.join(ROOT, "telescope_b200", "data")
+    out = str(tmp_path)
+    cli.main(["assign", os.path.join(data, "alignment.bam"), os.path.join(data, "annotation.gtf"), "--outdir", out, "--quiet",
+              "--updated_sam"])
+    g = np.load(os.path.join(GOLD, "bundled.npz"))
+    ck = np.load(os.path.join(out, "telescope-checkpoint.npz"), allow_pickle=True)
+    o = EMOracle(g["indptr"], g["indices"], g["raw"], int(g["shape"][1]), 1e-7, 100, 0, 200000).em()
+    shape = tuple(int(v) for v in g["shape"])
+    z = sp.csr_matrix((o.z, g["indices"], g["indptr"]), shape=shape).todok()
+    mat = sp.csr_matrix((o.reassign_data("exclude", 0.9, False), g["indices"], g["indptr"]), shape=shape).todok()
+    read_index = {str(n): i for i, n in enumerate(ck["_read_list"])}          # checkpoint members, model.py:108-121
+    feat_index = {str(n): i for i, n in enumerate(ck["_feat_list"])}
+    assert np.array_equal(ck["_raw_scores_data"], g["raw"]) and np.array_equal(ck["_raw_scores_indices"], g["indices"])
+
+    def phred(p):
+        return int(round(-10 * np.log10(1 - p))) if p < 1.0 else 255
+    assert (phred(0.9), phred(0.999999), phred(0), phred(1)) == (10, 60, 0, 255)       # helpers.py:28-35
+    with bam.AlignmentReader(os.path.join(out, "telescope-updated.bam"), keep_raw=True) as r:
+        upd = list(r)
+    assert len(upd) == 66414
+    n_pri = n_assigned = 0
+    for s in upd:
+        mapq = s.raw[9]
+        if s.tags[b"ZT"] == "SEC":
+            assert s.flag & bam.FSECONDARY and s.tags[b"YC"] == "248,248,248" and mapq == 0
+            continue
+        n_pri += 1
+        i, j = read_index[s.name], feat_index[s.tags[b"ZF"]]
+        p = float(z.get((i, j), 0.0))
+        knife_edge = abs((p * 100) % 1 - 0.5) < 1e-9       # a posterior within 1e-11 of a rounding boundary (none here)
+        assert knife_edge or s.tags[b"XP"] == int(round(p * 100))
+        assert mapq == min(phred(p), 255) or knife_edge
+        if mat.get((i, j), 0) > 0:
+            n_assigned += 1
+            assert not (s.flag & bam.FSECONDARY) and s.tags[b"YC"] == "217,95,2"
+        else:
+            assert s.flag & bam.FSECONDARY and s.tags[b"YC"] == ("230,171,2" if p >= 0.2 else "209,236,228")
+    assert n_assigned == 2 * int(sum(mat.values())) and n_pri >= n_assigned
+
+
 def test_em_can_be_called_again_and_continues():
     g = np.load(os.path.join(GOLD, "case_cutoff.npz"))
     m, tl = _run(g)                       # 7 iterations

@@ -159,6 +159,8 @@ struct Shard {
     int4* ell_index = nullptr;            // per slice record: offset / 16, first locus, T | last locus << 8, reads
     int ell_grid = 0, ell_grid_lnl = 0;
     long long *ell_range = nullptr, *ell_range_lnl = nullptr;      // record boundaries of the CTAs (grid + 1 each)
+    int* ell_rowid = nullptr;             // 16 per slice: the shard's read in each slot (-1 = empty)
+    int* res_rowid = nullptr;             // per residual read: the shard's read
     long long res_amb_rows = 0, res_amb_nnz = 0;   // the ambiguous part of the residual CSR (it also holds the unique reads)
     long long res_rows = 0, res_nnz = 0, res_n_tiles = 0, res_n_long = 0;
     long long* res_indptr = nullptr;
@@ -291,6 +293,8 @@ static int launch_rows(int G, F&& f) {
 static Csr csr_of(const Shard& s) { return Csr{s.indptr, s.col, s.q, s.n_rows}; }
 
 static int launch_fused(tsc_handle* h, Shard& s, bool gated);
+static int launch_reassign_sums(tsc_handle* h, Shard& s, int method, double thresh, const double* ta, const double* tu,
+                                double* colsum, int* nbest_d);
 static int launch_lnl_kernels(tsc_handle* h, Shard& s, const EmState* st, const double* ta, const double* tu,
                               const double* ia, const double* iu, int* nparts_out);
 
@@ -313,6 +317,38 @@ static void launch_tiles(const Shard& s, const TileArgs& a, bool smem_tab, int l
         if (long8) k_tiles<MODE, false, true><<<grid, kTileThreads, scratch, s.stream>>>(a);
         else k_tiles<MODE, false, false><<<grid, kTileThreads, scratch, s.stream>>>(a);
     }
+}
+
+// reassign(method, thresh) column sums (into colsum, already zeroed; may be NULL) and / or best-hit counts per read
+// (nbest_d, may be NULL) of one shard, posterior from the tables (ta, tu).  Clustered-stream layout: the stream kernel
+// for its reads (lane = read: max / count / kept are private reductions) + the rows kernel on the residual CSR;
+// otherwise the rows kernel on the whole shard.  Not for TSC_CHOOSE with picks or per-entry output.
+static int launch_reassign_sums(tsc_handle* h, Shard& s, int method, double thresh, const double* ta, const double* tu,
+                                double* colsum, int* nbest_d) {
+    if (h->kernel == TSC_KERNEL_ELL) {
+        if (s.ell_slices > 0 && (colsum || nbest_d) && (method != TSC_UNIQUE || nbest_d)) {
+            EllArgs e{s.ell_stream, s.ell_index, s.ell_range, s.ell_slices, ta, colsum, h->K, 1, nullptr, nullptr, nullptr, nullptr,
+                      method, thresh, s.ell_rowid, nbest_d};
+            k_ell<ELL_REASSIGN><<<s.ell_grid, 32, ell_smem_bytes<ELL_REASSIGN>(), s.stream>>>(e);
+            LAUNCH(h);
+        }
+        if (s.res_rows > 0) {
+            ReassignArgs g{method, thresh, nullptr, nbest_d, colsum, nullptr, s.res_rowid};
+            const Csr rest{s.res_indptr, s.res_col, s.res_q, s.res_rows};
+            launch_rows(h->G, [&](auto gg) {
+                k_reassign_rows<decltype(gg)::value><<<s.grid_rows, 512, 0, s.stream>>>(rest, ta, tu, g);
+            });
+            LAUNCH(h);
+        }
+    } else {
+        ReassignArgs g{method, thresh, nullptr, nbest_d, colsum, nullptr, nullptr};
+        launch_rows(h->G, [&](auto gg) {
+            k_reassign_rows<decltype(gg)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, g);
+        });
+        LAUNCH(h);
+    }
+    CU(cudaGetLastError());
+    return TSC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------- small API
@@ -363,7 +399,7 @@ static void free_shard(Shard& s) {
     void* ptrs[] = {s.indptr, s.col, s.q, s.wy, s.tiles, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
                     s.pi_init, s.theta_init, s.pisum0, s.acc, s.thetasum, s.ones, s.tmp_a, s.tmp_b, s.tmp_c, s.colsum,
                     s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad,
-                    s.ell_stream, s.ell_index, s.ell_range, s.ell_range_lnl, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles, s.res_tiles_amb,
+                    s.ell_stream, s.ell_index, s.ell_range, s.ell_range_lnl, s.ell_rowid, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles, s.res_tiles_amb,
                     s.peer_ptrs_d, s.tail_partials, s.tail_ticket, s.peer_err, s.log_tab};
     for (void* p : ptrs) if (p && !s.in_slab(p)) cudaFree(p);
     for (auto& b : s.slabs) cudaFree(b.first);
@@ -738,7 +774,11 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         if ((rc = fetch_ll(s, bin_start + n_keys, &n_cand))) return rc;
         lap("  ell classify+hist+scan");
         if (n_cand > 0) {
-            CU(tmp.alloc(&sorted, n_cand));
+            // kept: slot -> read of every slice (best-hit counts of reassign go back to the reads through it)
+            const long long slots = ((n_cand + kEllReads - 1) / kEllReads) * kEllReads;
+            CU(cudaMalloc(&s.ell_rowid, sizeof(int) * slots));
+            CU(cudaMemsetAsync(s.ell_rowid, 0xff, sizeof(int) * slots, s.stream));
+            sorted = s.ell_rowid;
             k_ell_scatter<<<g, 256, 0, s.stream>>>(key, n_rows, bin_start, cursor, sorted);
             LAUNCH(h);
             CU(cudaGetLastError());
@@ -815,6 +855,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
                 rs.add(&s.res_col, (size_t)s.res_nnz + pad);
                 rs.add(&s.res_q, (size_t)s.res_nnz + pad);
                 rs.add(&s.res_wy, (size_t)s.res_rows);
+                rs.add(&s.res_rowid, (size_t)s.res_rows);
                 int rc = rs.commit(s);
                 if (rc) return rc;
             }
@@ -825,7 +866,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
                 CU(cudaMemcpyAsync(counters + 4, start, sizeof(start), cudaMemcpyHostToDevice, s.stream));
             }
             k_res_append<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, key, counters + 4,
-                                                                                     s.res_indptr, s.res_col, s.res_q, s.res_wy);
+                                                                                     s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_rowid);
             LAUNCH(h);
             CU(cudaMemcpyAsync(s.res_indptr + s.res_rows, &s.res_nnz, sizeof(long long), cudaMemcpyHostToDevice, s.stream));
             CU(cudaGetLastError());
@@ -1141,6 +1182,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             CU(cudaSetDevice(s.dev));
             CU(cudaFuncSetAttribute(k_ell<ELL_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEllSmem));
             CU(cudaFuncSetAttribute(k_ell<ELL_LNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ell_smem_bytes<ELL_LNL>()));
+            CU(cudaFuncSetAttribute(k_ell<ELL_REASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ell_smem_bytes<ELL_REASSIGN>()));
             Arena arena;        // the raw scores are dead once Q is built: their memory serves the clustering's temporaries
             CU(cudaStreamSynchronize(s.stream));
             if (s.raw && s.nnz > 0) { arena.base = (char*)s.raw; arena.cap = sizeof(uint16_t) * (size_t)s.nnz; }
@@ -1404,10 +1446,9 @@ extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float
                 h->launches = l0;             // counted below
             } break;
             case 3: {
-                ReassignArgs g{TSC_EXCLUDE, 0.9, nullptr, nullptr, s.colsum, nullptr};
-                launch_rows(h->G, [&](auto gg) {
-                    k_reassign_rows<decltype(gg)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, g);
-                });
+                const long long l0 = h->launches;
+                if (launch_reassign_sums(h, s, TSC_EXCLUDE, 0.9, ta, tu, s.colsum, nullptr)) err = cudaErrorUnknown;
+                h->launches = l0;             // counted below
             } break;
             default:
                 err = cudaErrorInvalidValue;
@@ -1456,7 +1497,7 @@ static int launch_fused(tsc_handle* h, Shard& s, bool gated) {
     } else if (h->kernel == TSC_KERNEL_ELL) {
         // the clustered stream, then whatever does not fit a slice through the flat tiles of the residual CSR
         if (s.ell_slices > 0) {
-            EllArgs e{s.ell_stream, s.ell_index, s.ell_range, s.ell_slices, s.pt, s.acc, h->K, h->R_used, st, nullptr, nullptr, nullptr};
+            EllArgs e{s.ell_stream, s.ell_index, s.ell_range, s.ell_slices, s.pt, s.acc, h->K, h->R_used, st, nullptr, nullptr, nullptr, 0, 0.0, nullptr, nullptr};
             k_ell<ELL_FUSED><<<s.ell_grid, 32, kEllSmem, s.stream>>>(e);
             LAUNCH(h);
         }
@@ -1489,7 +1530,7 @@ static int launch_lnl_kernels(tsc_handle* h, Shard& s, const EmState* st, const 
     a.tab_amb = ta; a.tab_uni = tu; a.inner_amb = ia; a.inner_uni = iu; a.K = h->K; a.st = st; a.log_tab = s.log_tab;
     if (h->kernel == TSC_KERNEL_ELL) {
         if (s.ell_slices > 0) {
-            EllArgs e{s.ell_stream, s.ell_index, s.ell_range_lnl, s.ell_slices, ta, nullptr, h->K, 1, st, ia, s.partials, s.log_tab};
+            EllArgs e{s.ell_stream, s.ell_index, s.ell_range_lnl, s.ell_slices, ta, nullptr, h->K, 1, st, ia, s.partials, s.log_tab, 0, 0.0, nullptr, nullptr};
             k_ell<ELL_LNL><<<s.ell_grid_lnl, 32, ell_smem_bytes<ELL_LNL>(), s.stream>>>(e);
             LAUNCH(h);
             nparts = s.ell_grid_lnl;
@@ -1847,14 +1888,18 @@ static int reassign_impl(tsc_handle* h, int method, double thresh, int initial, 
         if (e == cudaSuccess && data) e = cudaMalloc(&data_d, sizeof(double) * std::max<long long>(s.nnz, 1));
         if (e == cudaSuccess && colsum) e = cudaMemsetAsync(s.colsum, 0, sizeof(double) * K, s.stream);
         if (e == cudaSuccess) {
-            ReassignArgs g{method, thresh, picks_d, nbest_d, colsum ? s.colsum : nullptr, data_d};
             const double* ta = initial ? s.ones : s.pt_prev;
             const double* tu = initial ? s.ones : s.pi_prev;
-            launch_rows(h->G, [&](auto gg) {
-                k_reassign_rows<decltype(gg)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, g);
-            });
-            LAUNCH(h);
-            e = cudaGetLastError();
+            if (!data_d && !picks_d) {          // column sums / best-hit counts only: the stream serves them
+                if (launch_reassign_sums(h, s, method, thresh, ta, tu, colsum ? s.colsum : nullptr, nbest_d)) e = cudaErrorUnknown;
+            } else {
+                ReassignArgs g{method, thresh, picks_d, nbest_d, colsum ? s.colsum : nullptr, data_d, nullptr};
+                launch_rows(h->G, [&](auto gg) {
+                    k_reassign_rows<decltype(gg)::value><<<s.grid_rows, 512, 0, s.stream>>>(csr_of(s), ta, tu, g);
+                });
+                LAUNCH(h);
+                e = cudaGetLastError();
+            }
         }
         if (e == cudaSuccess && nbest_h) { e = cudaMemcpyAsync(nbest_h + s.row_begin, nbest_d, sizeof(int) * s.n_rows, cudaMemcpyDeviceToHost, s.stream); h->d2h += sizeof(int) * s.n_rows; }
         if (e == cudaSuccess && data) { e = cudaMemcpyAsync(data + s.nnz_begin, data_d, sizeof(double) * s.nnz, cudaMemcpyDeviceToHost, s.stream); h->d2h += sizeof(double) * s.nnz; }

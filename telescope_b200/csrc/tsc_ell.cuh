@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict_
                                                     const double* __restrict__ q, const double* __restrict__ wy,
                                                     const int* __restrict__ key, unsigned long long* __restrict__ cursor,
                                                     long long* __restrict__ ip_out, int* __restrict__ col_out,
-                                                    double* __restrict__ q_out, double* __restrict__ wy_out) {
+                                                    double* __restrict__ q_out, double* __restrict__ wy_out,
+                                                    int* __restrict__ rowid_out) {
     const int lane = threadIdx.x & 7;
     const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
     long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict_
         old = __shfl_sync(gmask, old, (threadIdx.x & 31) & ~7);
         if (!res) continue;
         const long long rp = (long long)(old >> kResShift), o = (long long)(old & ((1ULL << kResShift) - 1ULL));
-        if (lane == 0) { ip_out[rp] = o; wy_out[rp] = wy[r]; }
+        if (lane == 0) { ip_out[rp] = o; wy_out[rp] = wy[r]; rowid_out[rp] = (int)r; }
         for (long long k = b + lane; k < e; k += 8) { col_out[o + (k - b)] = col[k]; q_out[o + (k - b)] = q[k]; }
     }
 }
@@ -309,7 +310,10 @@ __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict_
 //   ELL_FUSED : E-step + M-step sums (the per-iteration kernel; model.py:718-722 + 730-733)
 //   ELL_LNL   : log-likelihood of the stream's reads, sum z * log1p(Q * inner[locus]) with z from the E-step table
 //               (model.py:744-760); the reads outside the stream go through k_tiles<TILE_LNL> on the residual CSR
-enum { ELL_FUSED = 0, ELL_LNL = 1 };
+//   ELL_REASSIGN : reassign(method, thresh, initial) column sums and best-hit counts of the stream's reads
+//               (model.py:808-865, sparse_plus.py:99-165); lane = read makes row max / best-hit count / kept mass
+//               private serial reductions plus one shuffle each
+enum { ELL_FUSED = 0, ELL_LNL = 1, ELL_REASSIGN = 2 };
 
 struct EllArgs {
     const unsigned char* stream;
@@ -323,11 +327,25 @@ struct EllArgs {
     const double* inner;          // LNL: pi*theta inside log1p
     double* partials;             // LNL: one partial sum per CTA
     const LogTab* log_tab;        // LNL
+    // REASSIGN: pt = the posterior's table (pi*theta of the last E-step, or all ones for Q.norm(1)); acc = colsum[K]
+    int method;                   // tsc_method; TSC_CHOOSE counts the reads with a single best hit (like exclude)
+    double thresh;
+    const int* rowid;             // 16 per slice: the caller-side (compacted) read of each slot, -1 = empty
+    int* nbest;                   // per read (optional): number of best hits
+};
+
+struct EllReassign {              // REASSIGN: per-slice view handed to the body
+    int method, want_colsum;
+    double thresh;
+    const int* rowid_slice;       // this slice's 16 reads
+    int* nbest;
+    int* s_cnt;                   // shared int window [kEllWin + 2] (exclude / all)
+    double* s_avg;                // shared fp64 window [kEllWin + 2], single copy, CAS adds (average)
 };
 
 template <int MODE>
 __host__ __device__ constexpr size_t ell_smem_bytes() {
-    return MODE == ELL_FUSED ? sizeof(double) * ((kEllWin + 2) * kEllReads + kEllWin + 8)
+    return MODE != ELL_LNL ? sizeof(double) * ((kEllWin + 2) * kEllReads + kEllWin + 8)
                              : sizeof(double) * 2 * (kEllWin + 8) + sizeof(LogTab) * kLogTab;
 }
 constexpr size_t kEllSmem = ell_smem_bytes<ELL_FUSED>();
@@ -362,7 +380,7 @@ __device__ __noinline__ double ell_lnl_slow(const unsigned char* __restrict__ re
 template <int MODE, int TM>
 __device__ __forceinline__ void ell_body(const unsigned char* __restrict__ rec, int T, int lane, const double* s_pt,
                                          unsigned char* accb /* FUSED: s_acc + 8 * (lane & 15) */,
-                                         const double* s_in, const LogTab* s_log, double& lnl_local) {
+                                         const double* s_in, const LogTab* s_log, double& lnl_local, const EllReassign& re) {
     const unsigned char* cp = rec + kEllHdr + lane;
     const double* qp = reinterpret_cast<const double*>(rec + kEllHdr + 32 * T) + lane;
     double w_mine = 1.0;
@@ -400,6 +418,49 @@ __device__ __forceinline__ void ell_body(const unsigned char* __restrict__ rec, 
         for (int t = 0; t < TM; ++t) n[t] = *reinterpret_cast<const double*>(accb + ao[t]) + n[t] * g;
 #pragma unroll
         for (int t = 0; t < TM; ++t) *reinterpret_cast<double*>(accb + ao[t]) = n[t];
+    } else if (MODE == ELL_REASSIGN) {
+        // z of the read, its maximum, how many entries reach it, and (conf) the mass at or above the threshold: private
+        // over the lane's entries, then one exchange with the other lane of the read
+        const double rr = recip0(sum);
+        double zmax = 0.0, kept = 0.0;
+#pragma unroll
+        for (int t = 0; t < TM; ++t) {
+            n[t] *= rr;
+            zmax = fmax(zmax, n[t]);
+            if (n[t] >= re.thresh) kept += n[t];
+        }
+        zmax = fmax(zmax, __shfl_xor_sync(0xffffffffu, zmax, 16));
+        kept += __shfl_xor_sync(0xffffffffu, kept, 16);
+        int nb = 0;
+#pragma unroll
+        for (int t = 0; t < TM; ++t) nb += (n[t] == zmax && n[t] != 0.0);
+        nb += __shfl_xor_sync(0xffffffffu, nb, 16);
+        if (re.nbest && lane < 16 && re.rowid_slice[lane] >= 0) re.nbest[re.rowid_slice[lane]] = nb;
+        if (re.want_colsum) {
+            if (re.method == 3) {                        // conf: every surviving entry, renormalised -> dense private columns
+                const double rk = recip0(kept);
+#pragma unroll
+                for (int t = 0; t < TM; ++t) {
+                    const double v = (n[t] >= re.thresh) ? n[t] * rk : 0.0;
+                    n[t] = *reinterpret_cast<const double*>(accb + ao[t] * (kEllReads * 8)) + v;
+                }
+#pragma unroll
+                for (int t = 0; t < TM; ++t) *reinterpret_cast<double*>(accb + ao[t] * (kEllReads * 8)) = n[t];
+            } else if (re.method == 2) {                 // average: 1/nbest on every best hit (a few per read)
+                const double v = nb > 0 ? 1.0 / (double)nb : 0.0;
+#pragma unroll
+                for (int t = 0; t < TM; ++t)
+                    if (n[t] == zmax && n[t] != 0.0) atomicAdd(re.s_avg + ao[t], v);
+            } else if (re.method == 5) {                 // all: one per stored entry with a positive posterior
+#pragma unroll
+                for (int t = 0; t < TM; ++t)
+                    if (n[t] > 0.0) atomicAdd(re.s_cnt + ao[t], 1);
+            } else if (re.method <= 1) {                 // exclude (and the untied part of choose): the single best hit
+#pragma unroll
+                for (int t = 0; t < TM; ++t)
+                    if (nb == 1 && n[t] == zmax && n[t] != 0.0) atomicAdd(re.s_cnt + ao[t], 1);
+            }                                            // unique (4): every read of the stream is ambiguous -> nothing
+        }
     } else {
         // straight-line: every entry takes the table-driven log; entries whose argument is outside its range (never,
         // in practice) are redone with the library log1p afterwards
@@ -427,7 +488,7 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
     // FUSED: s_acc [kEllWin + 2][kEllReads] (last two rows = dummies) | s_pt [kEllWin + 8] ([kEllWin..] = 0 for empty slots)
     // LNL:   s_pt [kEllWin + 8] | s_in [kEllWin + 8] | log table
     double* s_acc = reinterpret_cast<double*>(s_raw);
-    double* s_pt = (MODE == ELL_FUSED) ? s_acc + (kEllWin + 2) * kEllReads : s_acc;
+    double* s_pt = (MODE != ELL_LNL) ? s_acc + (kEllWin + 2) * kEllReads : s_acc;
     double* s_in = s_pt + kEllWin + 8;
     LogTab* s_log = reinterpret_cast<LogTab*>(s_in + kEllWin + 8);
     const int lane = threadIdx.x;
@@ -435,9 +496,11 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
     const int K = a.K;
     const double* __restrict__ pt = a.pt;
     const unsigned char* __restrict__ stream = a.stream;
-    double* my = (MODE == ELL_FUSED) ? a.acc + (size_t)(blockIdx.x % a.R) * K : nullptr;
+    double* my = (MODE != ELL_LNL && a.acc) ? a.acc + (size_t)(blockIdx.x % a.R) * K : nullptr;
     unsigned char* accb = reinterpret_cast<unsigned char*>(s_acc) + 8 * (lane & 15);
     double lnl_local = 0.0;
+    // REASSIGN: the count / average windows overlay the accumulator columns (one method per launch)
+    EllReassign re{a.method, a.acc != nullptr, a.thresh, nullptr, a.nbest, reinterpret_cast<int*>(s_acc), s_acc + kEllWin + 8};
 
     for (int i = lane; i < (int)(ell_smem_bytes<MODE>() / 8); i += 32) s_acc[i] = 0.0;     // accumulators, tables
     if (MODE == ELL_LNL) {
@@ -457,14 +520,20 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
         if (T) ell_prefetch_l2(stream + ((long long)(unsigned)v.x << 4), (unsigned)ell_record_bytes(T));
     };
     auto flush_block = [&](int b) {
-        const int row = ((b & 3) * 32 + lane) * kEllReads;
         double s = 0.0;
+        if (MODE == ELL_REASSIGN && a.method != 3) {         // single-copy windows: counts (exclude, all) or 1/nbest sums
+            const int w = (b & 3) * 32 + lane;
+            if (a.method == 2) { s = re.s_avg[w]; re.s_avg[w] = 0.0; }
+            else { s = (double)re.s_cnt[w]; re.s_cnt[w] = 0; }
+        } else {
+            const int row = ((b & 3) * 32 + lane) * kEllReads;
 #pragma unroll
-        for (int c = 0; c < kEllReads; ++c) s += s_acc[row + ((c + lane) & 15)];
+            for (int c = 0; c < kEllReads; ++c) s += s_acc[row + ((c + lane) & 15)];
 #pragma unroll
-        for (int c = 0; c < kEllReads; ++c) s_acc[row + ((c + lane) & 15)] = 0.0;
+            for (int c = 0; c < kEllReads; ++c) s_acc[row + ((c + lane) & 15)] = 0.0;
+        }
         const int j = b * 32 + lane;
-        if (j < K && s != 0.0) atomicAdd(my + j, s);
+        if (my && j < K && s != 0.0) atomicAdd(my + j, s);
     };
 
     int4 cur = load_batch(r_begin), nxt = load_batch(r_begin + 32);
@@ -492,7 +561,7 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
                 __syncwarp();
                 int first_new = lb;
                 if (Fb >= 0) {
-                    if (MODE == ELL_FUSED) {
+                    if (MODE != ELL_LNL) {
                         const int e = min(lb, Fb + 4);
                         for (int blk = Fb; blk < e; ++blk) flush_block(blk);
                     }
@@ -506,19 +575,20 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
                 Fb = lb;
                 __syncwarp();
             }
+            if (MODE == ELL_REASSIGN) re.rowid_slice = a.rowid + (b + c) * kEllReads;
             switch ((T + 3) >> 2) {
-                case 1: ell_body<MODE, 4>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
-                case 2: ell_body<MODE, 8>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
-                case 3: ell_body<MODE, 12>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
-                case 4: ell_body<MODE, 16>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
-                case 5: ell_body<MODE, 20>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
-                default: ell_body<MODE, 24>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local); break;
+                case 1: ell_body<MODE, 4>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local, re); break;
+                case 2: ell_body<MODE, 8>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local, re); break;
+                case 3: ell_body<MODE, 12>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local, re); break;
+                case 4: ell_body<MODE, 16>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local, re); break;
+                case 5: ell_body<MODE, 20>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local, re); break;
+                default: ell_body<MODE, 24>(rec, T, lane, s_pt, accb, s_in, s_log, lnl_local, re); break;
             }
         }
         cur = nxt;
         nxt = after;
     }
-    if (MODE == ELL_FUSED) {
+    if (MODE != ELL_LNL) {
         // ---- run done: hand the window to the global accumulator
         __syncwarp();
         if (Fb >= 0) for (int blk = Fb; blk < Fb + 4; ++blk) flush_block(blk);

@@ -443,6 +443,7 @@ struct ReassignArgs {
     int* nbest;           // per read
     double* colsum;       // K
     double* data;         // nnz
+    const int* rowid;     // optional: nbest is indexed by rowid[read] (residual CSR -> the shard's reads)
 };
 
 template <int G>
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(512) k_reassign_rows(Csr a, const double* __re
             nb += (zz == zmax && zz != 0.0);
         }
         nb = group_sum_int<G>(nb, m);
-        if (g.nbest && lane == 0) g.nbest[r] = nb;
+        if (g.nbest && lane == 0) g.nbest[g.rowid ? g.rowid[r] : r] = nb;
         if (!g.colsum && !g.data) continue;
         const int pick = (g.method == 1 && g.picks && nb > 1) ? g.picks[r] : 0;
         const double rkept = recip0(kept);

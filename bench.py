@@ -415,7 +415,8 @@ def main():
 
     line = None
     if rank == 0:
-        cfg = base_config(a, world, total_nnz, alg_bytes)
+        # (the same expression as the reference arm, so that both arms print an identical `config`)
+        cfg = base_config(a, world, total_nnz, total_nnz * 12.0 / world + (a.reads // world + 1) * 4.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <functional>
 #include <limits>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -567,6 +568,88 @@ static int setup_transport(tsc_handle* h, const tsc_config& cfg) {
     return TSC_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------- host -> device
+// cudaMemcpyAsync from ordinary (pageable) memory goes through the driver's single staging buffer at ~11 GB/s.  A
+// scipy caller hands over exactly such arrays, so large pageable sources are staged here instead: a few host threads
+// copy chunks into a process-wide pool of page-locked slots and queue the DMA of each chunk as soon as it is filled
+// (~40 GB/s on the 16-core host of a B200 box, against ~55 GB/s from memory that is already page-locked).
+struct StagePool {
+    static constexpr size_t kSlot = 8u << 20;
+    std::vector<void*> slots;
+    std::mutex mu;
+    int ensure(size_t n) {
+        std::lock_guard<std::mutex> g(mu);
+        while (slots.size() < n) {
+            void* p = nullptr;
+            if (cudaHostAlloc(&p, kSlot, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); break; }
+            slots.push_back(p);
+        }
+        return (int)slots.size();
+    }
+};
+static StagePool g_stage;
+static std::mutex g_stage_busy;        // one staged upload at a time per process (the slots are shared)
+
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// dst (device, on s.dev) <- src (host), in stream order on s.stream.  Returns once every byte has left `src`'s pages or
+// (pinned source) once the copy is queued.
+static int upload(tsc_handle* h, Shard& s, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return TSC_OK;
+    h->h2d += (long long)bytes;
+    int threads = (int)std::thread::hardware_concurrency() / std::max(1, h->n_procs * (int)h->shards.size());
+    threads = std::max(1, std::min(threads, 8));
+    if (bytes < (32u << 20) || host_is_pinned(src) || getenv("TELESCOPE_B200_NO_STAGING")) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.stream));
+        return TSC_OK;
+    }
+    std::lock_guard<std::mutex> busy(g_stage_busy);
+    const int n_slots = g_stage.ensure((size_t)2 * threads);
+    if (n_slots < 2) {      // no page-locked memory to be had: the plain path still works
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.stream));
+        return TSC_OK;
+    }
+    threads = std::min(threads, n_slots / 2);
+    const int slots_used = 2 * threads;                 // a slot is only ever touched by one thread
+    const size_t n_chunks = (bytes + StagePool::kSlot - 1) / StagePool::kSlot;
+    std::vector<cudaError_t> err(threads, cudaSuccess);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([&, t]() {
+            cudaError_t e = cudaSetDevice(s.dev);
+            cudaEvent_t ev[2] = {nullptr, nullptr};
+            for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+            bool used[2] = {false, false};
+            for (size_t i = t; i < n_chunks && e == cudaSuccess; i += threads) {
+                const int k = (int)((i / threads) & 1);                  // this thread's two slots alternate
+                void* slot = g_stage.slots[(size_t)t + (size_t)k * threads];
+                if (used[k]) e = cudaEventSynchronize(ev[k]);            // the DMA out of this slot has finished
+                if (e != cudaSuccess) break;
+                const size_t off = i * StagePool::kSlot, n = std::min(StagePool::kSlot, bytes - off);
+                memcpy(slot, (const char*)src + off, n);
+                e = cudaMemcpyAsync((char*)dst + off, slot, n, cudaMemcpyHostToDevice, s.stream);
+                if (e == cudaSuccess) e = cudaEventRecord(ev[k], s.stream);
+                used[k] = true;
+            }
+            for (int k = 0; k < 2; ++k) {
+                if (used[k] && e == cudaSuccess) e = cudaEventSynchronize(ev[k]);     // slots go back to the pool drained
+                if (ev[k]) cudaEventDestroy(ev[k]);
+            }
+            err[t] = e;
+        });
+    }
+    for (auto& th : pool) th.join();
+    (void)slots_used;
+    for (cudaError_t e : err)
+        if (e != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("staged upload: ") + cudaGetErrorString(e));
+    return TSC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------- create
 struct StageTimer {
     bool on;                 // TELESCOPE_B200_TIMING: print laps and synchronise at lap boundaries
@@ -1038,7 +1121,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             char* ip_native = nullptr;
             CU(ipbuf.alloc(&ip_native, ib * (s.n_rows + 1)));
             const char* src = slow ? (const char*)(ip_compact->data() + s.row_begin) : (const char*)indptr + ib * s.row_begin;
-            CU(cudaMemcpyAsync(ip_native, src, ib * (s.n_rows + 1), cudaMemcpyHostToDevice, s.stream));
+            { int rc = upload(h, s, ip_native, src, ib * (s.n_rows + 1)); if (rc) return rc; }
             const int g = grid_for(s.n_rows + 1, 256, s.n_sm * 16);
             if (ib == 4) k_indptr_prepare<int><<<g, 256, 0, s.stream>>>((const int*)ip_native, s.n_rows + 1, s.nnz_begin, s.indptr, s.bad);
             else k_indptr_prepare<long long><<<g, 256, 0, s.stream>>>((const long long*)ip_native, s.n_rows + 1, s.nnz_begin, s.indptr, s.bad);
@@ -1068,10 +1151,9 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             CU(cudaMemsetAsync(s.bad, 0, sizeof(int), s.stream));
         }
         tm.lap("  indptr up + prepare");
-        CU(cudaMemcpyAsync(raw_d[i], raw + s.nnz_begin, sizeof(uint16_t) * s.nnz, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaMemcpyAsync(colin_d[i], indices + s.nnz_begin, sizeof(int) * s.nnz, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaMemcpyAsync(lut_d[i], q_lut, sizeof(double) * lut_len, cudaMemcpyHostToDevice, s.stream));
-        h->h2d += (size_t)(slow ? 8 : indptr_bytes) * (s.n_rows + 1) + (sizeof(uint16_t) + sizeof(int)) * s.nnz + sizeof(double) * lut_len;
+        { int rc = upload(h, s, raw_d[i], raw + s.nnz_begin, sizeof(uint16_t) * s.nnz); if (rc) return rc; }
+        { int rc = upload(h, s, colin_d[i], indices + s.nnz_begin, sizeof(int) * s.nnz); if (rc) return rc; }
+        { int rc = upload(h, s, lut_d[i], q_lut, sizeof(double) * lut_len); if (rc) return rc; }
         if (tm.on) { cudaStreamSynchronize(s.stream); tm.lap("  entries H2D (sync for timing)"); }
         // tiles for the flat-tile passes, built on the device while the entry arrays are still arriving
         {

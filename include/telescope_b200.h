@@ -163,7 +163,7 @@ const char* tsc_create_laps(tsc_handle* h);
 int tsc_allreduce_f64(tsc_handle* h, double* inout, int32_t n, int32_t op);
 /* Diagnostic: device layout of local shard 0 as 8 int64: [0] bytes of the clustered slice stream of the fused kernel,
  * [1] slices, [2] reads in the stream, [3] stored entries in the stream, [4] reads / [5] entries of the residual CSR
- * (ambiguous reads that do not fit a slice), [6] CTAs of the stream kernel, [7] flat tiles of the whole shard */
+ * (ambiguous reads that do not fit the stream), [6] CTAs of the stream kernel, [7] long-read records (more than 48 entries) */
 int tsc_get_layout_stats(tsc_handle* h, int64_t* out8);
 /* launches = kernels this library launched since creation; bytes moved over PCIe by this handle */
 int tsc_get_counters(tsc_handle* h, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes);

@@ -156,10 +156,12 @@ struct Shard {
     LogTab* log_tab = nullptr;                  // table of log1p_big (tsc_kernels.cuh)
     // clustered sliced-ELL stream of the fused kernel (tsc_ell.cuh) + residual CSR for the reads it does not hold
     unsigned char* ell_stream = nullptr;
-    long long ell_bytes = 0, ell_slices = 0, ell_reads = 0, ell_entries = 0;
+    long long ell_bytes = 0, ell_slices = 0, ell_long = 0, ell_records = 0, ell_reads = 0, ell_entries = 0;
     int4* ell_index = nullptr;            // per slice record: offset / 16, first locus, T | last locus << 8, reads
     int ell_grid = 0, ell_grid_lnl = 0;
     long long *ell_range = nullptr, *ell_range_lnl = nullptr;      // record boundaries of the CTAs (grid + 1 each)
+    long long *ell_lrange = nullptr, *ell_lrange_lnl = nullptr;    // the same for the long-read kernel
+    int ell_lgrid = 0, ell_lgrid_lnl = 0;
     int* ell_rowid = nullptr;             // 16 per slice: the shard's read in each slot (-1 = empty)
     int* res_rowid = nullptr;             // per residual read: the shard's read
     long long res_amb_rows = 0, res_amb_nnz = 0;   // the ambiguous part of the residual CSR (it also holds the unique reads)
@@ -327,10 +329,17 @@ static void launch_tiles(const Shard& s, const TileArgs& a, bool smem_tab, int l
 static int launch_reassign_sums(tsc_handle* h, Shard& s, int method, double thresh, const double* ta, const double* tu,
                                 double* colsum, int* nbest_d) {
     if (h->kernel == TSC_KERNEL_ELL) {
-        if (s.ell_slices > 0 && (colsum || nbest_d) && (method != TSC_UNIQUE || nbest_d)) {
+        const bool wanted = (colsum || nbest_d) && (method != TSC_UNIQUE || nbest_d);
+        if (s.ell_slices > 0 && wanted) {
             EllArgs e{s.ell_stream, s.ell_index, s.ell_range, s.ell_slices, ta, colsum, h->K, 1, nullptr, nullptr, nullptr, nullptr,
                       method, thresh, s.ell_rowid, nbest_d};
             k_ell<ELL_REASSIGN><<<s.ell_grid, 32, ell_smem_bytes<ELL_REASSIGN>(), s.stream>>>(e);
+            LAUNCH(h);
+        }
+        if (s.ell_long > 0 && wanted) {
+            EllArgs e{s.ell_stream, s.ell_index + s.ell_slices, s.ell_lrange, s.ell_long, ta, colsum, h->K, 1, nullptr, nullptr, nullptr, nullptr,
+                      method, thresh, s.ell_rowid + s.ell_slices * kEllReads, nbest_d};
+            k_ell_long<ELL_REASSIGN><<<s.ell_lgrid, 32, ell_long_smem_bytes<ELL_REASSIGN>(), s.stream>>>(e);
             LAUNCH(h);
         }
         if (s.res_rows > 0) {
@@ -400,7 +409,7 @@ static void free_shard(Shard& s) {
     void* ptrs[] = {s.indptr, s.col, s.q, s.wy, s.tiles, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
                     s.pi_init, s.theta_init, s.pisum0, s.acc, s.thetasum, s.ones, s.tmp_a, s.tmp_b, s.tmp_c, s.colsum,
                     s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad,
-                    s.ell_stream, s.ell_index, s.ell_range, s.ell_range_lnl, s.ell_rowid, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles, s.res_tiles_amb,
+                    s.ell_stream, s.ell_index, s.ell_range, s.ell_range_lnl, s.ell_lrange, s.ell_lrange_lnl, s.ell_rowid, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles, s.res_tiles_amb,
                     s.peer_ptrs_d, s.tail_partials, s.tail_ticket, s.peer_err, s.log_tab};
     for (void* p : ptrs) if (p && !s.in_slab(p)) cudaFree(p);
     for (auto& b : s.slabs) cudaFree(b.first);
@@ -819,6 +828,8 @@ static int fetch_ll(Shard& s, const long long* dev, long long* host) {
     return TSC_OK;
 }
 
+constexpr bool kLongRecordsDefault = false;     // long-read records in the stream (k_ell_long); see DESIGN.md
+
 // The clustered sliced-ELL stream of the fused kernel and the residual CSR (tsc_ell.cuh), from the shard's finished
 // q / col / indptr / wy arrays.  One-off; what it keeps belongs to the shard.  `arena`: dead device memory (the raw
 // upload buffers) that serves the temporaries.
@@ -835,11 +846,14 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
     unsigned long long* counters = nullptr;
     CU(tmp.alloc(&counters, 8));
     CU(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 8, s.stream));
-    const bool ell_ok = n_rows > 0 && (long long)K * (1 << kEllLenBits) < (1LL << 31);
-    long long n_cand = 0;
+    const long long n_short_keys_ll = (long long)K << kEllLenBits, n_keys_ll = n_short_keys_ll + K;
+    const bool ell_ok = n_rows > 0 && n_keys_ll < (1LL << 31);
+    long long n_short = 0, n_long = 0;
+    int n_stream_keys = 0x7fffffff;             // keys at or above this are not in the stream after all
     int* sorted = nullptr;
+    long long slots_short = 0;
     if (ell_ok) {
-        const int n_keys = K << kEllLenBits;
+        const int n_short_keys = (int)n_short_keys_ll, n_keys = (int)n_keys_ll;
         unsigned *hist = nullptr, *cursor = nullptr;
         long long* bin_start = nullptr;
         CU(tmp.alloc(&key, n_rows));
@@ -849,40 +863,55 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         CU(cudaMemsetAsync(hist, 0, sizeof(unsigned) * n_keys, s.stream));
         CU(cudaMemsetAsync(cursor, 0, sizeof(unsigned) * n_keys, s.stream));
         const int g = grid_for(n_rows, 256, s.n_sm * 16);
-        k_ell_classify<<<g, 256, 0, s.stream>>>(s.indptr, n_rows, s.col, n_keys, key, hist);
+        k_ell_classify<<<g, 256, 0, s.stream>>>(s.indptr, n_rows, s.col, n_short_keys, n_keys, key, hist);
         LAUNCH(h);
         CU(cudaGetLastError());
         int rc = device_scan<unsigned>(h, s, hist, n_keys, bin_start, arena);
         if (rc) return rc;
+        long long n_cand = 0;
+        if ((rc = fetch_ll(s, bin_start + n_short_keys, &n_short))) return rc;
         if ((rc = fetch_ll(s, bin_start + n_keys, &n_cand))) return rc;
+        n_long = n_cand - n_short;
+        // a handful of long reads is not worth a launch per pass: they stay with the flat tiles of the residual
+        const char* lr_env = getenv("TELESCOPE_B200_LONG_RECORDS");      // 0 / 1 overrides the default
+        const bool long_records = lr_env ? atoi(lr_env) != 0 : kLongRecordsDefault;
+        if (!long_records || n_long * 1000 < n_rows) { n_long = 0; n_cand = n_short; n_stream_keys = n_short_keys; }
         lap("  ell classify+hist+scan");
         if (n_cand > 0) {
-            // kept: slot -> read of every slice (best-hit counts of reassign go back to the reads through it)
-            const long long slots = ((n_cand + kEllReads - 1) / kEllReads) * kEllReads;
-            CU(cudaMalloc(&s.ell_rowid, sizeof(int) * slots));
-            CU(cudaMemsetAsync(s.ell_rowid, 0xff, sizeof(int) * slots, s.stream));
+            // kept: slot -> read of every slice, then the long reads (best-hit counts of reassign go back through it);
+            // the short slots are padded to whole slices
+            slots_short = ((n_short + kEllReads - 1) / kEllReads) * kEllReads;
+            CU(cudaMalloc(&s.ell_rowid, sizeof(int) * (slots_short + n_long)));
+            CU(cudaMemsetAsync(s.ell_rowid, 0xff, sizeof(int) * (slots_short + n_long), s.stream));
             sorted = s.ell_rowid;
-            k_ell_scatter<<<g, 256, 0, s.stream>>>(key, n_rows, bin_start, cursor, sorted);
+            k_ell_scatter<<<g, 256, 0, s.stream>>>(key, n_rows, bin_start, cursor, sorted, n_short_keys, n_stream_keys, slots_short - n_short);
             LAUNCH(h);
             CU(cudaGetLastError());
         }
     }
-    if (n_cand > 0) {
-        const long long n_slices = (n_cand + kEllReads - 1) / kEllReads;
+    if (n_short + n_long > 0) {
+        const long long n_slices = slots_short / kEllReads, n_records = n_slices + n_long;
         int* rec_bytes = nullptr;
         long long* rec_off = nullptr;
-        CU(cudaMalloc(&s.ell_index, sizeof(int4) * n_slices));      // kept: the kernel's record index
-        CU(tmp.alloc(&rec_bytes, n_slices));
-        CU(tmp.alloc(&rec_off, (size_t)n_slices + 1));
+        CU(cudaMalloc(&s.ell_index, sizeof(int4) * n_records));      // kept: the kernels' record index
+        CU(tmp.alloc(&rec_bytes, n_records));
+        CU(tmp.alloc(&rec_off, (size_t)n_records + 1));
         lap("  ell scatter");
-        k_ell_slices<<<grid_for(n_slices, 128, s.n_sm * 16), 128, 0, s.stream>>>(s.indptr, s.col, sorted, n_cand, n_slices, key,
-                                                                                s.ell_index, rec_bytes);
-        LAUNCH(h);
+        if (n_slices > 0) {
+            k_ell_slices<<<grid_for(n_slices, 128, s.n_sm * 16), 128, 0, s.stream>>>(s.indptr, s.col, sorted, n_short, n_slices, key,
+                                                                                    s.ell_index, rec_bytes);
+            LAUNCH(h);
+        }
+        if (n_long > 0) {
+            k_ell_long_index<<<grid_for(n_long, 128, s.n_sm * 16), 128, 0, s.stream>>>(s.indptr, s.col, sorted + slots_short, n_long,
+                                                                                      s.ell_index + n_slices, rec_bytes + n_slices);
+            LAUNCH(h);
+        }
         CU(cudaGetLastError());
-        int rc = device_scan<int>(h, s, rec_bytes, n_slices, rec_off, arena);
+        int rc = device_scan<int>(h, s, rec_bytes, n_records, rec_off, arena);
         if (rc) return rc;
         long long total = 0;
-        if ((rc = fetch_ll(s, rec_off + n_slices, &total))) return rc;
+        if ((rc = fetch_ll(s, rec_off + n_records, &total))) return rc;
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ell<ELL_FUSED>, 32, kEllSmem));
         int per_sm_lnl = 0;
@@ -892,20 +921,42 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         if (total >= (1LL << 36)) return fail(TSC_ERR_ARG, "slice stream of one GPU exceeds 64 GB");
         CU(cudaMalloc(&s.ell_stream, (size_t)total));
         lap("  ell stream malloc");
-        k_ell_fill<<<grid_for(n_slices * 32, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, s.col, s.q, s.wy, sorted, n_cand, n_slices,
-                                                                                   s.ell_index, rec_off, s.ell_stream);
-        LAUNCH(h);
+        if (n_slices > 0) {
+            k_ell_fill<<<grid_for(n_slices * 32, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, s.col, s.q, s.wy, sorted, n_short, n_slices,
+                                                                                       s.ell_index, rec_off, s.ell_stream);
+            LAUNCH(h);
+        }
+        if (n_long > 0) {
+            k_ell_fill_long<<<grid_for(n_long * 32, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, s.col, s.q, s.wy, sorted + slots_short,
+                                                                                          n_long, s.ell_index + n_slices, rec_off + n_slices,
+                                                                                          s.ell_stream);
+            LAUNCH(h);
+        }
         CU(cudaGetLastError());
         s.ell_bytes = total;
         s.ell_slices = n_slices;
-        // every resident warp gets a contiguous, byte-balanced run (at least ~8 records each when the stream is short)
-        s.ell_grid = (int)std::max<long long>(1, std::min<long long>((n_slices + 7) / 8, warps));
-        s.ell_grid_lnl = (int)std::max<long long>(1, std::min<long long>((n_slices + 7) / 8, (long long)s.n_sm * std::max(per_sm_lnl, 1)));
-        CU(cudaMalloc(&s.ell_range, sizeof(long long) * (s.ell_grid + 1)));
-        CU(cudaMalloc(&s.ell_range_lnl, sizeof(long long) * (s.ell_grid_lnl + 1)));
-        k_ell_ranges<<<(s.ell_grid + 256) / 256, 256, 0, s.stream>>>(rec_off, n_slices, s.ell_grid, s.ell_range);
-        k_ell_ranges<<<(s.ell_grid_lnl + 256) / 256, 256, 0, s.stream>>>(rec_off, n_slices, s.ell_grid_lnl, s.ell_range_lnl);
-        h->launches += 2;
+        s.ell_long = n_long;
+        s.ell_records = n_records;
+        // every resident warp gets a contiguous, byte-balanced run (at least ~8 records each when the stream is short);
+        // slices and long reads have a kernel (and a split) each
+        auto split = [&](const long long* off, long long n, int cap, int* grid, long long** range) -> int {
+            *grid = (int)std::max<long long>(1, std::min<long long>((n + 7) / 8, cap));
+            CU(cudaMalloc(range, sizeof(long long) * (*grid + 1)));
+            k_ell_ranges<<<(*grid + 256) / 256, 256, 0, s.stream>>>(off, n, *grid, *range);
+            LAUNCH(h);
+            return TSC_OK;
+        };
+        if (n_slices > 0) {
+            if ((rc = split(rec_off, n_slices, warps, &s.ell_grid, &s.ell_range))) return rc;
+            if ((rc = split(rec_off, n_slices, s.n_sm * std::max(per_sm_lnl, 1), &s.ell_grid_lnl, &s.ell_range_lnl))) return rc;
+        }
+        if (n_long > 0) {
+            int pl = 0, pl_lnl = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pl, k_ell_long<ELL_FUSED>, 32, ell_long_smem_bytes<ELL_FUSED>()));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pl_lnl, k_ell_long<ELL_LNL>, 32, ell_long_smem_bytes<ELL_LNL>()));
+            if ((rc = split(rec_off + n_slices, n_long, s.n_sm * std::max(pl, 1), &s.ell_lgrid, &s.ell_lrange))) return rc;
+            if ((rc = split(rec_off + n_slices, n_long, s.n_sm * std::max(pl_lnl, 1), &s.ell_lgrid_lnl, &s.ell_lrange_lnl))) return rc;
+        }
         CU(cudaGetLastError());
         lap("  ell fill");
     }
@@ -915,7 +966,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
     // give: the order of the residual's reads is irrelevant, only each read's entries stay together.
     {
         const int g = grid_for(n_rows, 256, s.n_sm * 16);
-        k_res_count<<<g, 256, 0, s.stream>>>(s.indptr, n_rows, key, counters);
+        k_res_count<<<g, 256, 0, s.stream>>>(s.indptr, n_rows, key, n_stream_keys, counters);
         LAUNCH(h);
         CU(cudaGetLastError());
         unsigned long long cnt[4];
@@ -948,7 +999,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
                 const unsigned long long start[2] = {0ULL, ((unsigned long long)s.res_amb_rows << kResShift) | (unsigned long long)s.res_amb_nnz};
                 CU(cudaMemcpyAsync(counters + 4, start, sizeof(start), cudaMemcpyHostToDevice, s.stream));
             }
-            k_res_append<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, key, counters + 4,
+            k_res_append<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, key, n_stream_keys, counters + 4,
                                                                                      s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_rowid);
             LAUNCH(h);
             CU(cudaMemcpyAsync(s.res_indptr + s.res_rows, &s.res_nnz, sizeof(long long), cudaMemcpyHostToDevice, s.stream));
@@ -1104,7 +1155,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             small.add(&s.consts, 1);
             small.add(&s.st, 1);
             small.add(&s.scalars, 8);
-            small.add(&s.partials, (size_t)s.n_sm * 64);
+            small.add(&s.partials, (size_t)s.n_sm * 96);
             small.add(&s.log_tab, (size_t)kLogTab);
             rc = small.commit(s);
             if (rc) return rc;
@@ -1265,6 +1316,9 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             CU(cudaFuncSetAttribute(k_ell<ELL_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEllSmem));
             CU(cudaFuncSetAttribute(k_ell<ELL_LNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ell_smem_bytes<ELL_LNL>()));
             CU(cudaFuncSetAttribute(k_ell<ELL_REASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ell_smem_bytes<ELL_REASSIGN>()));
+            CU(cudaFuncSetAttribute(k_ell_long<ELL_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ell_long_smem_bytes<ELL_FUSED>()));
+            CU(cudaFuncSetAttribute(k_ell_long<ELL_LNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ell_long_smem_bytes<ELL_LNL>()));
+            CU(cudaFuncSetAttribute(k_ell_long<ELL_REASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ell_long_smem_bytes<ELL_REASSIGN>()));
             Arena arena;        // the raw scores are dead once Q is built: their memory serves the clustering's temporaries
             CU(cudaStreamSynchronize(s.stream));
             if (s.raw && s.nnz > 0) { arena.base = (char*)s.raw; arena.cap = sizeof(uint16_t) * (size_t)s.nnz; }
@@ -1449,7 +1503,7 @@ extern "C" int tsc_get_layout_stats(tsc_handle* h, int64_t* out8) {
     if (!h || !out8) return fail(TSC_ERR_ARG, "NULL argument");
     const Shard& s = h->shards[0];
     out8[0] = s.ell_bytes; out8[1] = s.ell_slices; out8[2] = s.ell_reads; out8[3] = s.ell_entries;
-    out8[4] = s.res_amb_rows; out8[5] = s.res_amb_nnz; out8[6] = s.ell_grid; out8[7] = s.n_tiles;
+    out8[4] = s.res_amb_rows; out8[5] = s.res_amb_nnz; out8[6] = s.ell_grid; out8[7] = s.ell_long;
     return TSC_OK;
 }
 
@@ -1583,6 +1637,11 @@ static int launch_fused(tsc_handle* h, Shard& s, bool gated) {
             k_ell<ELL_FUSED><<<s.ell_grid, 32, kEllSmem, s.stream>>>(e);
             LAUNCH(h);
         }
+        if (s.ell_long > 0) {
+            EllArgs e{s.ell_stream, s.ell_index + s.ell_slices, s.ell_lrange, s.ell_long, s.pt, s.acc, h->K, h->R_used, st, nullptr, nullptr, nullptr, 0, 0.0, nullptr, nullptr};
+            k_ell_long<ELL_FUSED><<<s.ell_lgrid, 32, ell_long_smem_bytes<ELL_FUSED>(), s.stream>>>(e);
+            LAUNCH(h);
+        }
         if (s.res_amb_rows > 0) {         // (a residual of unique reads only has nothing to add)
             TileArgs a{};
             a.tiles = s.res_tiles_amb; a.n_tiles = s.res_amb_tiles; a.q = s.res_q; a.col = s.res_col; a.wy = s.res_wy; a.tab_amb = s.pt;
@@ -1616,6 +1675,13 @@ static int launch_lnl_kernels(tsc_handle* h, Shard& s, const EmState* st, const 
             k_ell<ELL_LNL><<<s.ell_grid_lnl, 32, ell_smem_bytes<ELL_LNL>(), s.stream>>>(e);
             LAUNCH(h);
             nparts = s.ell_grid_lnl;
+        }
+        if (s.ell_long > 0) {
+            EllArgs e{s.ell_stream, s.ell_index + s.ell_slices, s.ell_lrange_lnl, s.ell_long, ta, nullptr, h->K, 1, st, ia, s.partials + nparts,
+                      s.log_tab, 0, 0.0, nullptr, nullptr};
+            k_ell_long<ELL_LNL><<<s.ell_lgrid_lnl, 32, ell_long_smem_bytes<ELL_LNL>(), s.stream>>>(e);
+            LAUNCH(h);
+            nparts += s.ell_lgrid_lnl;
         }
         if (s.res_rows > 0) {
             a.tiles = s.res_tiles; a.n_tiles = s.res_n_tiles; a.q = s.res_q; a.col = s.res_col; a.partials = s.partials + nparts;

@@ -30,9 +30,15 @@
 // empty slots add an exact +0.0 to a word nobody reads.
 // With one byte per locus the stream moves ~9.5 B per entry where canonical CSR moves 12.
 //
-// Reads that do not fit a slice (fewer than 2 or more than 2*kEllTMax entries, a locus span above kEllSpan, or
-// non-increasing loci) are not in the stream: unique reads add nothing to the M-step sums (model.py:730-733; they
-// enter pi through pisum0, model.py:699,738) and the rest go through the flat-tile kernel on a compact residual CSR.
+// Long reads (more than 2*kEllTMax = 48 entries; real multi-mappers of large TE families, the Zipf configuration) follow
+// the slices in the same stream as ONE RECORD PER READ, `wy, pad | uint16 window-row[nch][32] | fp64 Q[nch][32]`, and
+// have their own kernel (k_ell_long): the whole warp works on one read (lane l owns entries l, l+32, ...; the row sum is a
+// warp reduction), the window is a single copy of 1024 loci in the same 17 KB of shared memory -- within one read the
+// loci are distinct, so plain read-modify-write again, no atomics.
+//
+// Reads that fit neither form (a locus span above kEllSpan / kLongSpan, non-increasing loci) are not in the stream, and
+// neither are the unique reads: those add nothing to the M-step sums (model.py:730-733; they enter pi through pisum0,
+// model.py:699,738).  Both live in a compact residual CSR for the flat-tile kernels (ambiguous ones in front).
 #pragma once
 #include "tsc_kernels.cuh"
 
@@ -48,11 +54,19 @@ constexpr int kEllHdr = kEllReads * 8;        // wy
 #endif
 constexpr int kEllAhead = TSC_ELL_AHEAD;      // records between the L2 prefetch and the loads
 constexpr int kEllLenBits = 6;                // sort key = first locus << 6 | snake(length)
+// long reads (more than 2*kEllTMax entries): one read per record, the whole warp on it, a single-copy window
+constexpr int kLongWin = 1024;                // loci in the warp's window in long mode (32 blocks of 32)
+constexpr int kLongSpan = kLongWin - 32;      // max (last - first locus) of a long read
+constexpr int kLongChunks = 127;              // chunks of 32 entries per long record (7 bits of the index word)
+constexpr int kLongRegs = 8;                  // chunks kept in registers (reads of up to 256 entries: one pass)
 static_assert(2 * kEllTMax < (1 << kEllLenBits), "length must fit the key");
 static_assert(kEllTMax == 24, "k_ell_fused dispatches bodies of 4..24 steps");
 static_assert(kEllAhead >= 1 && kEllAhead < 32, "prefetch distance is within one segment");
 
 __host__ __device__ inline int ell_record_bytes(int T) { return kEllHdr + 288 * T; }
+__host__ __device__ inline int ell_long_bytes(int nch) { return 16 + 320 * nch; }      // wy, pad | u16 row[nch][32] | q[nch][32]
+// the T byte of an index entry: 1..kEllTMax = slice of 16 reads with T steps; 0x80 | nch = one long read of nch chunks
+__host__ __device__ inline int ell_bytes_of(int tbyte) { return (tbyte & 0x80) ? ell_long_bytes(tbyte & 0x7f) : ell_record_bytes(tbyte); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // exclusive prefix sums (construction only): out[i] = sum in[0..i), out[n] = total.  4096 items per block.
@@ -128,26 +142,29 @@ __global__ void k_scan_add(long long* __restrict__ out, long long n, const long 
 // construction of the clustered stream
 // ---------------------------------------------------------------------------------------------------------------
 
-// Per read: the sort key of a slice candidate (first locus, then length in snake order so that neighbouring keys
-// hold reads of similar length), or -1; candidates are counted per key.
-__global__ void k_ell_classify(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ col, int n_keys,
-                               int* __restrict__ key, unsigned* __restrict__ hist) {
+// Per read: the sort key of a stream candidate, or -1; candidates are counted per key.  Short reads (2..48 entries):
+// (first locus, length in snake order, so that neighbouring keys hold reads of similar length) -> 16 of them share a
+// slice.  Long reads (49..4064 entries, loci increasing, span <= kLongSpan): n_short_keys + first locus -> a record each.
+__global__ void k_ell_classify(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ col, int n_short_keys,
+                               int n_keys, int* __restrict__ key, unsigned* __restrict__ hist) {
     long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; r < n_rows; r += stride) {
         const long long s = ip[r], e = ip[r + 1];
         const long long len = e - s;
         int k = -1;
-        if (len >= 2 && len <= 2 * kEllTMax) {
+        if (len >= 2 && len <= 32 * kLongChunks) {
             const int first = col[s];
             bool ok = true;
             int prev = first;
             for (long long p = s + 1; p < e; ++p) { const int c = col[p]; ok = ok && (c > prev); prev = c; }
-            if (ok && prev - first <= kEllSpan) {
+            if (ok && len <= 2 * kEllTMax && prev - first <= kEllSpan) {
                 const int lk = (first & 1) ? ((1 << kEllLenBits) - 1 - (int)len) : (int)len;
                 k = (first << kEllLenBits) | lk;
-                if (k >= n_keys) k = -1;      // cannot happen for first < n_cols; keeps the histogram in bounds
+            } else if (ok && len > 2 * kEllTMax && prev - first <= kLongSpan) {
+                k = n_short_keys + first;
             }
+            if (k >= n_keys) k = -1;          // cannot happen for first < n_cols; keeps the histogram in bounds
         }
         key[r] = k;
         if (k >= 0) atomicAdd(hist + k, 1u);
@@ -157,14 +174,55 @@ __global__ void k_ell_classify(const long long* __restrict__ ip, long long n_row
 // Counting-sort scatter: candidates land in key order (order inside a key is whatever the atomics give; all reads
 // of a key have the same first locus and length, so only the summation order inside a slice depends on it).
 __global__ void k_ell_scatter(const int* __restrict__ key, long long n_rows, const long long* __restrict__ bin_start,
-                              unsigned* __restrict__ cursor, int* __restrict__ sorted) {
+                              unsigned* __restrict__ cursor, int* __restrict__ sorted, int n_short_keys, int n_stream_keys,
+                              long long long_pad) {
     long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; r < n_rows; r += stride) {
         const int k = key[r];
-        if (k < 0) continue;
-        const long long pos = bin_start[k] + atomicAdd(cursor + k, 1u);
+        if (k < 0 || k >= n_stream_keys) continue;
+        long long pos = bin_start[k] + atomicAdd(cursor + k, 1u);
+        if (k >= n_short_keys) pos += long_pad;        // the short slots are padded to whole slices
         sorted[pos] = (int)r;
+    }
+}
+
+// Index entries of the long reads: one record each.
+__global__ void k_ell_long_index(const long long* __restrict__ ip, const int* __restrict__ col, const int* __restrict__ sorted_long,
+                                 long long n_long, int4* __restrict__ hdr, int* __restrict__ rec_bytes) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n_long; i += stride) {
+        const int r = sorted_long[i];
+        const long long b = ip[r], e = ip[r + 1];
+        const int nch = (int)((e - b + 31) >> 5);
+        hdr[i] = make_int4(0, col[b], (0x80 | nch) | (col[e - 1] << 8), 1);
+        rec_bytes[i] = ell_long_bytes(nch);
+    }
+}
+
+// One warp per long read writes its record and completes its index entry.
+__global__ void __launch_bounds__(256) k_ell_fill_long(const long long* __restrict__ ip, const int* __restrict__ col,
+                                                       const double* __restrict__ q, const double* __restrict__ wy,
+                                                       const int* __restrict__ sorted_long, long long n_long,
+                                                       int4* __restrict__ hdr, const long long* __restrict__ rec_off,
+                                                       unsigned char* __restrict__ stream) {
+    const int lane = threadIdx.x & 31;
+    long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (; i < n_long; i += stride) {
+        const int r = sorted_long[i];
+        const long long b = ip[r], off = rec_off[i];
+        const int len = (int)(ip[r + 1] - b), nch = (len + 31) >> 5;
+        unsigned char* rec = stream + off;
+        if (lane == 0) { hdr[i].x = (int)(off >> 4); reinterpret_cast<double*>(rec)[0] = wy[r]; reinterpret_cast<double*>(rec)[1] = 0.0; }
+        unsigned short* wc = reinterpret_cast<unsigned short*>(rec + 16);
+        double* qq = reinterpret_cast<double*>(rec + 16 + 64 * nch);
+        for (int k = lane; k < nch * 32; k += 32) {
+            const bool real = k < len;
+            wc[k] = (unsigned short)(real ? (col[b + k] & (kLongWin - 1)) : (kLongWin + lane));      // empty: this lane's dummy word
+            qq[k] = real ? q[b + k] : 0.0;
+        }
     }
 }
 
@@ -200,10 +258,10 @@ __global__ void k_ell_slices(const long long* __restrict__ ip, const int* __rest
 __global__ void k_ell_ranges(const long long* __restrict__ rec_off, long long n_slices, int n_ctas, long long* __restrict__ range) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w > n_ctas) return;
-    const long long total = rec_off[n_slices];
+    const long long base = rec_off[0], total = rec_off[n_slices] - base;
     const long long target = (w == n_ctas) ? total : (long long)((__int128)total * w / n_ctas);
-    long long lo = 0, hi = n_slices;          // first record with rec_off >= target
-    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (rec_off[mid] < target) lo = mid + 1; else hi = mid; }
+    long long lo = 0, hi = n_slices;          // first record that starts at or after the target
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (rec_off[mid] - base < target) lo = mid + 1; else hi = mid; }
     range[w] = lo;
 }
 
@@ -242,12 +300,13 @@ __global__ void __launch_bounds__(256) k_ell_fill(const long long* __restrict__ 
     }
 }
 
-// Residual CSR = the reads that are not in the stream: key < 0 (key == nullptr: everybody), unique reads included.
+// Residual CSR = the reads that are not in the stream: key < 0 or >= n_stream_keys (key == nullptr: everybody), unique
+// reads included.
 // counters[0] += ambiguous reads, [1] += their entries, [2] += (1 << kResShift | entries) per residual read,
 // [3] += the same for the ambiguous residual reads.
 constexpr int kResShift = 38;     // a cursor packs (reads << 38 | entries): < 2^26 reads and < 2^38 entries per GPU
 
-__global__ void k_res_count(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ key,
+__global__ void k_res_count(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ key, int n_stream_keys,
                             unsigned long long* __restrict__ counters) {
     unsigned long long rows = 0, ents = 0, res = 0, res_amb = 0;
     long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -255,7 +314,7 @@ __global__ void k_res_count(const long long* __restrict__ ip, long long n_rows, 
     for (; r < n_rows; r += stride) {
         const long long len = ip[r + 1] - ip[r];
         if (len >= 2) { ++rows; ents += (unsigned long long)len; }
-        if (key == nullptr || key[r] < 0) {
+        if (key == nullptr || key[r] < 0 || key[r] >= n_stream_keys) {
             res += (1ULL << kResShift) | (unsigned long long)len;
             if (len >= 2) res_amb += (1ULL << kResShift) | (unsigned long long)len;
         }
@@ -280,7 +339,8 @@ __global__ void k_res_count(const long long* __restrict__ ip, long long n_rows, 
 // the residual (the fused kernel only visits those), unique reads the rest: cursor[1] starts where the front ends.
 __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ col,
                                                     const double* __restrict__ q, const double* __restrict__ wy,
-                                                    const int* __restrict__ key, unsigned long long* __restrict__ cursor,
+                                                    const int* __restrict__ key, int n_stream_keys,
+                                                    unsigned long long* __restrict__ cursor,
                                                     long long* __restrict__ ip_out, int* __restrict__ col_out,
                                                     double* __restrict__ q_out, double* __restrict__ wy_out,
                                                     int* __restrict__ rowid_out) {
@@ -292,7 +352,7 @@ __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict_
     for (; r < r_end; r += stride) {
         long long b = 0, e = 0;
         bool res = false;
-        if (r < n_rows) { b = ip[r]; e = ip[r + 1]; res = (key == nullptr || key[r] < 0); }
+        if (r < n_rows) { b = ip[r]; e = ip[r + 1]; res = (key == nullptr || key[r] < 0 || key[r] >= n_stream_keys); }
         unsigned long long old = 0;     // cursor[0]: ambiguous reads (the front of the residual), cursor[1]: unique reads
         if (res && lane == 0) old = atomicAdd(cursor + ((e - b >= 2) ? 0 : 1), (1ULL << kResShift) | (unsigned long long)(e - b));
         old = __shfl_sync(gmask, old, (threadIdx.x & 31) & ~7);
@@ -330,7 +390,7 @@ struct EllArgs {
     // REASSIGN: pt = the posterior's table (pi*theta of the last E-step, or all ones for Q.norm(1)); acc = colsum[K]
     int method;                   // tsc_method; TSC_CHOOSE counts the reads with a single best hit (like exclude)
     double thresh;
-    const int* rowid;             // 16 per slice: the caller-side (compacted) read of each slot, -1 = empty
+    const int* rowid;             // slices: 16 per record, the shard's read of each slot (-1 = empty); long reads: 1 per record
     int* nbest;                   // per read (optional): number of best hits
 };
 
@@ -343,10 +403,14 @@ struct EllReassign {              // REASSIGN: per-slice view handed to the body
     double* s_avg;                // shared fp64 window [kEllWin + 2], single copy, CAS adds (average)
 };
 
+// Shared memory of a one-warp CTA of the slice kernels (doubles): acc [kEllWin + 2][16] | pt [kEllWin + 8], or
+// (LNL) pt [kEllWin + 8] | inner [kEllWin + 8] | log table.  The long-read kernels: ell_long_smem_bytes.
+constexpr int kShortDoubles = (kEllWin + 2) * kEllReads + kEllWin + 8;
+constexpr int kLongDoubles = 2 * (kLongWin + 32);
 template <int MODE>
 __host__ __device__ constexpr size_t ell_smem_bytes() {
-    return MODE != ELL_LNL ? sizeof(double) * ((kEllWin + 2) * kEllReads + kEllWin + 8)
-                             : sizeof(double) * 2 * (kEllWin + 8) + sizeof(LogTab) * kLogTab;
+    return MODE != ELL_LNL ? sizeof(double) * kShortDoubles
+                           : sizeof(double) * 2 * (kEllWin + 8) + sizeof(LogTab) * kLogTab;
 }
 constexpr size_t kEllSmem = ell_smem_bytes<ELL_FUSED>();
 
@@ -481,6 +545,147 @@ __device__ __forceinline__ void ell_body(const unsigned char* __restrict__ rec, 
     }
 }
 
+// ---- long reads: one read per record, lane l owns entries l, l + 32, ...; window = single-copy arrays of kLongWin loci
+struct EllLongWin {
+    double* acc;                  // [kLongWin + 32] (FUSED / REASSIGN); the last 32 = one dummy word per lane
+    const double* pt;             // [kLongWin + 32], dummies = 0
+    const double* in;             // LNL: [kLongWin + 32]
+};
+
+__device__ __forceinline__ double warp_sum(double v) { return group_sum<32>(v, 0xffffffffu); }
+__device__ __forceinline__ double warp_max(double v) { return group_max<32>(v, 0xffffffffu); }
+__device__ __forceinline__ int warp_sum_int(int v) { return group_sum_int<32>(v, 0xffffffffu); }
+
+// what a long read adds at an entry with posterior z (REASSIGN; model.py:837-862)
+__device__ __forceinline__ double ell_reassign_value(int method, double z, double zmax, int nb, double thresh, double rkept) {
+    const bool best = (z == zmax && z != 0.0);
+    switch (method) {
+        case 0: case 1: return (best && nb == 1) ? 1.0 : 0.0;
+        case 2: return best ? 1.0 / (double)nb : 0.0;
+        case 3: return (z >= thresh) ? z * rkept : 0.0;
+        case 5: return (z > 0.0) ? 1.0 : 0.0;
+        default: return 0.0;          // unique: a long read is ambiguous
+    }
+}
+
+// nch <= NC chunks, everything in registers: one pass over the record
+template <int MODE, int NC>
+__device__ __forceinline__ void ell_long(const unsigned char* __restrict__ rec, int nch, int lane, const EllLongWin& w,
+                                         const LogTab* s_log, double& lnl_local, const EllReassign& re) {
+    const unsigned short* wp = reinterpret_cast<const unsigned short*>(rec + 16) + lane;
+    const double* qp = reinterpret_cast<const double*>(rec + 16 + 64 * nch) + lane;
+    double n[NC];
+    unsigned row[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        n[c] = 0.0;
+        row[c] = kLongWin + lane;                       // this lane's dummy word
+        if (c < 2 || c < nch) { row[c] = __ldg(wp + 32 * c); n[c] = ell_ld_stream(qp + 32 * c); }
+    }
+    double x[MODE == ELL_LNL ? NC : 1];
+    double sum = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (MODE == ELL_LNL) x[c] = n[c] * w.in[row[c]];
+        n[c] *= w.pt[row[c]];
+        sum += n[c];
+    }
+    sum = warp_sum(sum);
+    if (MODE == ELL_FUSED) {
+        const double wy = __ldg(reinterpret_cast<const double*>(rec));
+        const double g = (wy != 0.0) ? wy * recip0(sum) : 0.0;
+        // loci are unique within a read and every empty slot has its own dummy word: plain read-modify-write
+#pragma unroll
+        for (int c = 0; c < NC; ++c) n[c] = w.acc[row[c]] + n[c] * g;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) w.acc[row[c]] = n[c];
+    } else if (MODE == ELL_REASSIGN) {
+        const double rr = recip0(sum);
+        double zmax = 0.0, kept = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { n[c] *= rr; zmax = fmax(zmax, n[c]); if (n[c] >= re.thresh) kept += n[c]; }
+        zmax = warp_max(zmax);
+        kept = warp_sum(kept);
+        int nb = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) nb += (n[c] == zmax && n[c] != 0.0);
+        nb = warp_sum_int(nb);
+        if (re.nbest && lane == 0 && re.rowid_slice[0] >= 0) re.nbest[re.rowid_slice[0]] = nb;
+        if (re.want_colsum) {
+            const double rk = recip0(kept);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) n[c] = w.acc[row[c]] + ell_reassign_value(re.method, n[c], zmax, nb, re.thresh, rk);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) w.acc[row[c]] = n[c];
+        }
+    } else {
+        const double rr = recip0(sum);
+        double acc2[2] = {0.0, 0.0};
+        bool slow = false;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const double xt = x[MODE == ELL_LNL ? c : 0];
+            n[c] *= rr;
+            const double term = n[c] * log_big_core(xt, s_log);
+            const bool use = n[c] != 0.0, ok = log_big_ok(xt);
+            acc2[c & 1] += (use && ok) ? term : 0.0;
+            slow = slow || (use && !ok);
+        }
+        lnl_local += acc2[0] + acc2[1];
+        if (__any_sync(0xffffffffu, slow)) {
+#pragma unroll 1
+            for (int c = 0; c < nch; ++c) {             // rare: recomputed from the record, library log1p
+                const unsigned r2 = wp[32 * c];
+                const double qv = qp[32 * c], z = (qv * w.pt[r2]) * rr, xt = qv * w.in[r2];
+                if (z != 0.0 && !log_big_ok(xt)) lnl_local += z * log1p(xt);
+            }
+        }
+    }
+}
+
+// more than kLongRegs chunks (reads above 256 entries): the record is walked once per reduction (L2 hits)
+template <int MODE>
+__device__ __noinline__ void ell_long_big(const unsigned char* __restrict__ rec, int nch, int lane, const EllLongWin& w,
+                                          const LogTab* s_log, double& lnl_local, const EllReassign& re) {
+    const unsigned short* wp = reinterpret_cast<const unsigned short*>(rec + 16) + lane;
+    const double* qp = reinterpret_cast<const double*>(rec + 16 + 64 * nch) + lane;
+    double sum = 0.0;
+    for (int c = 0; c < nch; ++c) sum += qp[32 * c] * w.pt[wp[32 * c]];
+    sum = warp_sum(sum);
+    const double rr = recip0(sum);
+    if (MODE == ELL_FUSED) {
+        const double wy = __ldg(reinterpret_cast<const double*>(rec));
+        const double g = (wy != 0.0) ? wy * rr : 0.0;
+        for (int c = 0; c < nch; ++c) { const unsigned r2 = wp[32 * c]; w.acc[r2] += (qp[32 * c] * w.pt[r2]) * g; }
+    } else if (MODE == ELL_LNL) {
+        for (int c = 0; c < nch; ++c) {
+            const unsigned r2 = wp[32 * c];
+            const double qv = qp[32 * c], z = (qv * w.pt[r2]) * rr;
+            if (z != 0.0) lnl_local += z * log1p_big(qv * w.in[r2], s_log);
+        }
+    } else {
+        double zmax = 0.0, kept = 0.0;
+        for (int c = 0; c < nch; ++c) {
+            const double z = (qp[32 * c] * w.pt[wp[32 * c]]) * rr;
+            zmax = fmax(zmax, z);
+            if (z >= re.thresh) kept += z;
+        }
+        zmax = warp_max(zmax);
+        kept = warp_sum(kept);
+        int nb = 0;
+        for (int c = 0; c < nch; ++c) { const double z = (qp[32 * c] * w.pt[wp[32 * c]]) * rr; nb += (z == zmax && z != 0.0); }
+        nb = warp_sum_int(nb);
+        if (re.nbest && lane == 0 && re.rowid_slice[0] >= 0) re.nbest[re.rowid_slice[0]] = nb;
+        if (re.want_colsum) {
+            const double rk = recip0(kept);
+            for (int c = 0; c < nch; ++c) {
+                const unsigned r2 = wp[32 * c];
+                w.acc[r2] += ell_reassign_value(re.method, (qp[32 * c] * w.pt[r2]) * rr, zmax, nb, re.thresh, rk);
+            }
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -594,6 +799,114 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
         if (Fb >= 0) for (int blk = Fb; blk < Fb + 4; ++blk) flush_block(blk);
     }
     if (MODE == ELL_LNL) {
+        lnl_local = group_sum<32>(lnl_local, 0xffffffffu);
+        if (lane == 0) a.partials[blockIdx.x] = lnl_local;
+    }
+}
+
+
+// ---- the same passes over the long-read records (their own launch: the slice kernel stays free of the mode logic)
+template <int MODE>
+__host__ __device__ constexpr size_t ell_long_smem_bytes() {
+    return sizeof(double) * kLongDoubles + (MODE == ELL_LNL ? sizeof(LogTab) * kLogTab : 0);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32) k_ell_long(const EllArgs a) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    if (a.st && a.st->done) return;
+    // FUSED / REASSIGN: acc [kLongWin + 32] | pt [kLongWin + 32];   LNL: pt | inner | log table
+    double* l_acc = reinterpret_cast<double*>(s_raw);
+    double* l_pt = (MODE != ELL_LNL) ? l_acc + kLongWin + 32 : l_acc;
+    double* l_in = l_pt + kLongWin + 32;
+    LogTab* s_log = reinterpret_cast<LogTab*>(l_acc + kLongDoubles);
+    const int lane = threadIdx.x;
+    const long long r_begin = a.range[blockIdx.x], r_end = a.range[blockIdx.x + 1];     // this warp's run of long reads
+    const int K = a.K;
+    const double* __restrict__ pt = a.pt;
+    const unsigned char* __restrict__ stream = a.stream;
+    double* my = (MODE != ELL_LNL && a.acc) ? a.acc + (size_t)(blockIdx.x % a.R) * K : nullptr;
+    double lnl_local = 0.0;
+    EllReassign re{a.method, a.acc != nullptr, a.thresh, nullptr, a.nbest, nullptr, nullptr};
+    const EllLongWin lw{l_acc, l_pt, l_in};
+    constexpr int kBlocks = kLongWin / 32;
+
+    for (int i = lane; i < kLongDoubles; i += 32) l_acc[i] = 0.0;
+    if (MODE == ELL_LNL)
+        for (int i = lane; i < kLogTab; i += 32) s_log[i] = a.log_tab[i];
+    __syncwarp();
+
+    auto load_batch = [&](long long b) -> int4 {
+        int4 v = make_int4(0, 0, 0, 0);
+        if (b + lane < r_end) v = __ldg(a.index + b + lane);
+        return v;
+    };
+    auto prefetch_mine = [&](const int4& v) {
+        const int tb = v.z & 0xff;
+        if (tb) ell_prefetch_l2(stream + ((long long)(unsigned)v.x << 4), (unsigned)ell_bytes_of(tb));
+    };
+    auto flush_block = [&](int blk) {
+        const int w = (blk & (kBlocks - 1)) * 32 + lane;
+        const double s = l_acc[w];
+        l_acc[w] = 0.0;
+        const int j = blk * 32 + lane;
+        if (my && j < K && s != 0.0) atomicAdd(my + j, s);
+    };
+
+    int4 cur = load_batch(r_begin), nxt = load_batch(r_begin + 32);
+    if (lane < kEllAhead) prefetch_mine(cur);
+    int Fb = -1;                                      // first block (32 loci) of the window; -1 = empty
+
+    for (long long b = r_begin; b < r_end; b += 32) {
+        const int4 after = load_batch(b + 64);
+        const int nrec = (int)min(32LL, r_end - b);
+        for (int c = 0; c < nrec; ++c) {
+            {
+                const int pc = c + kEllAhead;
+                if (lane == (pc & 31)) prefetch_mine(pc < 32 ? cur : nxt);
+            }
+            const unsigned off16 = (unsigned)__shfl_sync(0xffffffffu, cur.x, c);
+            const int lo = __shfl_sync(0xffffffffu, cur.y, c);
+            const int thi = __shfl_sync(0xffffffffu, cur.z, c);
+            const int nch = thi & 0x7f, hi = thi >> 8;
+            const unsigned char* rec = stream + ((long long)off16 << 4);
+            // ---- window: blocks [Fb, Fb + 32) of 32 loci; the long reads are sorted by first locus
+            const int lb = lo >> 5;
+            if (Fb < 0 || (hi >> 5) >= Fb + kBlocks) {
+                __syncwarp();
+                int first_new = lb;
+                if (Fb >= 0) {
+                    if (MODE != ELL_LNL) {
+                        const int e = min(lb, Fb + kBlocks);
+                        for (int blk = Fb; blk < e; ++blk) flush_block(blk);
+                    }
+                    first_new = max(lb, Fb + kBlocks);
+                }
+                for (int blk = first_new; blk < lb + kBlocks; ++blk) {
+                    const int j = blk * 32 + lane, w = (blk & (kBlocks - 1)) * 32 + lane;
+                    l_pt[w] = (j < K) ? __ldg(pt + j) : 0.0;
+                    if (MODE == ELL_LNL) l_in[w] = (j < K) ? __ldg(a.inner + j) : 0.0;
+                }
+                Fb = lb;
+                __syncwarp();
+            }
+            if (MODE == ELL_REASSIGN) re.rowid_slice = a.rowid + (b + c);
+            switch ((nch + 1) >> 1) {
+                case 1: ell_long<MODE, 2>(rec, nch, lane, lw, s_log, lnl_local, re); break;
+                case 2: ell_long<MODE, 4>(rec, nch, lane, lw, s_log, lnl_local, re); break;
+                case 3: ell_long<MODE, 6>(rec, nch, lane, lw, s_log, lnl_local, re); break;
+                case 4: ell_long<MODE, 8>(rec, nch, lane, lw, s_log, lnl_local, re); break;
+                default: ell_long_big<MODE>(rec, nch, lane, lw, s_log, lnl_local, re); break;
+            }
+            __syncwarp();          // the next read touches the same window words from other lanes
+        }
+        cur = nxt;
+        nxt = after;
+    }
+    if (MODE != ELL_LNL) {
+        __syncwarp();
+        if (Fb >= 0) for (int blk = Fb; blk < Fb + kBlocks; ++blk) flush_block(blk);
+    } else {
         lnl_local = group_sum<32>(lnl_local, 0xffffffffu);
         if (lane == 0) a.partials[blockIdx.x] = lnl_local;
     }

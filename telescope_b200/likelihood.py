@@ -342,7 +342,7 @@ class TelescopeLikelihood(object):
         buf = (C.c_int64 * 8)()
         _abi.check(self._lib.tsc_get_layout_stats(self._h, buf))
         names = ("stream_bytes", "slices", "stream_reads", "stream_entries", "residual_reads", "residual_entries",
-                 "stream_ctas", "tiles")
+                 "stream_ctas", "long_reads")
         return dict(zip(names, (int(v) for v in buf)))
 
     def counters(self):

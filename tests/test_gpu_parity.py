@@ -497,6 +497,57 @@ def test_small_scores_take_the_library_log1p(kernel):
     tl.close()
 
 
+def test_ell_long_read_records(monkeypatch):
+    """Reads of more than 48 entries live in the stream as one record each (csrc/tsc_ell.cuh, long mode): 49 entries (two
+    chunks), 256 / 257 (registers / walked), locus spans of 992 (fits the 1024-locus window) and 993 (residual), dense
+    groups and isolated first loci (window advances inside long mode), mixed with short reads so that a warp's run crosses
+    the slice -> long-read boundary.  EM, log-likelihood, every reassign mode and the best-hit counts against the oracle."""
+    monkeypatch.setenv("TELESCOPE_B200_LONG_RECORDS", "1")
+    rng = np.random.default_rng(303)
+    K = 3000
+    rows = []
+
+    def run(first, n, span):
+        mid = np.sort(rng.choice(np.arange(first + 1, first + span), n - 2, replace=False))
+        return np.concatenate(([first], mid, [first + span])).astype(np.int64)
+
+    for first in (0, 7, 500, 501, 1900):
+        for _ in range(30):
+            n = int(rng.integers(49, 300))
+            rows.append(run(first, n, int(rng.integers(n - 1, 993))))
+    rows.append(run(3, 49, 48)); rows.append(run(3, 49, 992)); rows.append(run(3, 49, 993))
+    rows.append(run(11, 256, 700)); rows.append(run(11, 257, 700)); rows.append(run(11, 993, 992))
+    for first in range(100, K - 1000, 211):
+        rows.append(run(first, int(rng.integers(49, 120)), int(rng.integers(200, 993))))
+    for _ in range(600):                                        # short reads around the same loci
+        f = int(rng.integers(0, K - 100)); n = int(rng.integers(1, 40))
+        rows.append(np.array([f]) if n == 1 else run(f, n, int(rng.integers(n - 1, 97))))
+    order = rng.permutation(len(rows))
+    rows = [rows[i] for i in order]
+    lens = [len(r) for r in rows]
+    indptr = np.cumsum([0] + lens)
+    indices = np.concatenate(rows).astype(np.int32)
+    raw = (150 + rng.integers(0, 60, indices.size)).astype(np.uint16)
+    m = sp.csr_matrix((raw, indices, indptr), shape=(len(rows), K))
+    opts = Opts(max_iter=5)
+    tl, o = _tl(m, opts, kernel="ell"), _oracle(m, opts)
+    st = tl.layout_stats()
+    assert st["long_reads"] >= 150 and st["residual_reads"] >= 1 and st["slices"] >= 10
+    tl.em(use_likelihood=True); o.em(use_likelihood=True)
+    assert tl.n_iter == o.n_iter
+    assert rel_err(tl.pi, o.pi) < TIGHT and rel_err(tl.theta, o.theta) < TIGHT and rel_err(tl.lnls, o.lnls) < TIGHT
+    for method, initial in [("exclude", False), ("exclude", True), ("all", False), ("all", True), ("unique", False)]:
+        assert np.array_equal(tl.reassign_colsum(method, 0.9, initial), o.reassign_colsum(method, 0.9, initial)), (method, initial)
+    for method, initial in [("conf", False), ("average", False), ("average", True), ("conf", True)]:
+        assert rel_err(tl.reassign_colsum(method, 0.3, initial), o.reassign_colsum(method, 0.3, initial)) < RTOL, (method, initial)
+    np.random.seed(5)
+    a = tl.reassign_colsum("choose", 0.9, True)
+    np.random.seed(5)
+    b = o.reassign_colsum("choose", 0.9, True)
+    assert np.array_equal(a, b)
+    tl.close()
+
+
 def test_ell_handles_unsorted_columns_through_the_residual_path():
     """Non-canonical CSR (loci not increasing inside a read) must not enter a slice: the stream relies on distinct,
     increasing loci per read."""

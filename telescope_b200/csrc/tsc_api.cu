@@ -4,13 +4,15 @@
 // csr_matrix_plus helpers it calls (telescope/utils/sparse_plus.py:16-165).  No CPU fallback: every compute entry
 // point needs a CUDA device and fails loudly otherwise.
 //
-// Layout in HBM, per shard (= one GPU's contiguous block of reads):
-//   q[nnz] fp64, col[nnz] int32 (internal locus numbering: descending entry count, so hot loci are low indices),
-//   indptr[rows+1] int64, wy[rows] fp64 (= w_i * Y_i), tiles[~nnz/115] 32-byte descriptors for the fused kernel,
-//   and K-length fp64 vectors: pi, theta, pt (= pi*theta), their *_prev twins (the parameters the stored posterior
-//   z was computed from, model.py:795), *_init, pisum0, thetasum, R accumulator replicas.
-// Per EM iteration and shard: fused E+M kernel -> replica reduce -> [NCCL all-reduce of K doubles] -> update kernel.
-// The loop runs ahead of the host; convergence is decided on the device and polled through pinned memory.
+// Layout in HBM, per shard (= one GPU's contiguous block of reads; DESIGN.md section 3):
+//   q[nnz] fp64, col[nnz] int32 (the caller's locus numbering), indptr[rows+1] int64, wy[rows] fp64 (= w_i * Y_i),
+//   tiles[~nnz/115] 32-byte descriptors of the flat-tile passes; the clustered slice stream + its record index (what
+//   the per-iteration kernel reads) and the residual CSR of the reads outside it; K-length fp64 vectors: pi, theta,
+//   pt (= pi*theta), their *_prev twins (the parameters the stored posterior z was computed from, model.py:795),
+//   *_init, pisum0, accumulator replicas; the exchange buffer every rank of the node maps.
+// Per EM iteration and shard: stream kernel (+ flat tiles on the residual front) -> k_tail (replica sum, exchange
+// between the GPUs through peer memory, update, loop control).  The loop runs ahead of the host; convergence is decided
+// on the device and polled through pinned memory.
 #include <algorithm>
 #include <chrono>
 #include <cmath>

@@ -1,11 +1,14 @@
 // Device code of libtelescope_b200: Telescope's EM reassignment path on sm_100a.
 //
-// Two families of kernels work on the same HBM-resident CSR shard (fp64 Q values, int32 locus indices, int64 row
-// pointers, one shard per GPU):
-//   * "rows" kernels  -- one sub-warp of G lanes per read.  Simple; used for every one-off pass (init, posterior
-//     export, log-likelihood, the six reassign modes) and as the in-library cross-check of the fast path.
-//   * "tiles" kernel  -- the per-iteration fused E+M step (tsc_tiles.cuh): flat 128-entry tiles, 128-bit loads,
-//     warp segmented scan, scatter-add of z*w into L2-resident accumulator replicas.
+// Kernel families over one HBM-resident shard (fp64 Q values, int32 locus indices, int64 row pointers per GPU):
+//   * "rows" kernels (this file) -- one sub-warp of G lanes per read.  Simple; used for construction, per-entry outputs
+//     (reassign data), the residual of the reassign sums, and as the in-library cross-check of the fast paths.
+//   * "tiles" kernel (tsc_tiles.cuh) -- flat tiles of whole reads (<= 128 entries), one warp per tile, lane-consecutive
+//     loads, one blocked segmented scan: posterior export (writes z), and the fused / log-likelihood passes over the reads
+//     that are not in the clustered stream.
+//   * "stream" kernels (tsc_ell.cuh) -- the per-iteration fused E+M step, the log-likelihood and the reassign sums over
+//     the locus-clustered sliced-ELL copy of the ambiguous reads; (tsc_peer.cuh) the per-iteration tail with the exchange
+//     between GPUs.
 //
 // Arithmetic follows the reference's operation order wherever it changes bits (compiled with -fmad=false):
 //   n = Q * (pi*theta)  or  Q * pi          telescope/utils/model.py:718-720

@@ -830,7 +830,7 @@ static int fetch_ll(Shard& s, const long long* dev, long long* host) {
     return TSC_OK;
 }
 
-constexpr bool kLongRecordsDefault = false;     // long-read records in the stream (k_ell_long); see DESIGN.md
+constexpr bool kLongRecordsDefault = true;     // long-read records in the stream (k_ell_long); see DESIGN.md
 
 // The clustered sliced-ELL stream of the fused kernel and the residual CSR (tsc_ell.cuh), from the shard's finished
 // q / col / indptr / wy arrays.  One-off; what it keeps belongs to the shard.  `arena`: dead device memory (the raw
@@ -956,8 +956,10 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
             int pl = 0, pl_lnl = 0;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pl, k_ell_long<ELL_FUSED>, 32, ell_long_smem_bytes<ELL_FUSED>()));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pl_lnl, k_ell_long<ELL_LNL>, 32, ell_long_smem_bytes<ELL_LNL>()));
-            if ((rc = split(rec_off + n_slices, n_long, s.n_sm * std::max(pl, 1), &s.ell_lgrid, &s.ell_lrange))) return rc;
-            if ((rc = split(rec_off + n_slices, n_long, s.n_sm * std::max(pl_lnl, 1), &s.ell_lgrid_lnl, &s.ell_lrange_lnl))) return rc;
+            // (the long-read kernel deals batches of 32 records round-robin: no run table)
+            const long long batches = (n_long + 31) / 32;
+            s.ell_lgrid = (int)std::max<long long>(1, std::min<long long>(batches, (long long)s.n_sm * std::max(pl, 1)));
+            s.ell_lgrid_lnl = (int)std::max<long long>(1, std::min<long long>(batches, (long long)s.n_sm * std::max(pl_lnl, 1)));
         }
         CU(cudaGetLastError());
         lap("  ell fill");

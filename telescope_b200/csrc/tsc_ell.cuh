@@ -55,7 +55,8 @@ constexpr int kEllHdr = kEllReads * 8;        // wy
 constexpr int kEllAhead = TSC_ELL_AHEAD;      // records between the L2 prefetch and the loads
 constexpr int kEllLenBits = 6;                // sort key = first locus << 6 | snake(length)
 // long reads (more than 2*kEllTMax entries): one read per record, the whole warp on it, a single-copy window
-constexpr int kLongWin = 1024;                // loci in the warp's window in long mode (32 blocks of 32)
+constexpr int kLongWin = 512;                 // loci in the warp's window of the long-read kernel (16 blocks of 32): 8.5 KB per
+                                              // one-warp CTA, so ~20 warps per SM hide the latency of one-read-at-a-time work
 constexpr int kLongSpan = kLongWin - 32;      // max (last - first locus) of a long read
 constexpr int kLongChunks = 127;              // chunks of 32 entries per long record (7 bits of the index word)
 constexpr int kLongRegs = 8;                  // chunks kept in registers (reads of up to 256 entries: one pass)
@@ -568,71 +569,86 @@ __device__ __forceinline__ double ell_reassign_value(int method, double z, doubl
     }
 }
 
-// nch <= NC chunks, everything in registers: one pass over the record
+// nch <= NC chunks, everything in registers: one pass over the record, in two phases so that two reads can be in
+// flight per warp (their load and reduction chains are independent; only the window updates are ordered).
 template <int MODE, int NC>
-__device__ __forceinline__ void ell_long(const unsigned char* __restrict__ rec, int nch, int lane, const EllLongWin& w,
-                                         const LogTab* s_log, double& lnl_local, const EllReassign& re) {
-    const unsigned short* wp = reinterpret_cast<const unsigned short*>(rec + 16) + lane;
-    const double* qp = reinterpret_cast<const double*>(rec + 16 + 64 * nch) + lane;
+struct EllLongState {
     double n[NC];
     unsigned row[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        n[c] = 0.0;
-        row[c] = kLongWin + lane;                       // this lane's dummy word
-        if (c < 2 || c < nch) { row[c] = __ldg(wp + 32 * c); n[c] = ell_ld_stream(qp + 32 * c); }
-    }
     double x[MODE == ELL_LNL ? NC : 1];
-    double sum = 0.0;
+    double sum;
+};
+
+// phase 1: loads, numerators n = Q * (pi*theta)[locus], this lane's part of the row sum
+template <int MODE, int NC>
+__device__ __forceinline__ void ell_long_p1(EllLongState<MODE, NC>& st, const unsigned char* __restrict__ rec, int nch, int lane,
+                                            const EllLongWin w) {
+    const unsigned short* wp = reinterpret_cast<const unsigned short*>(rec + 16) + lane;
+    const double* qp = reinterpret_cast<const double*>(rec + 16 + 64 * nch) + lane;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        if (MODE == ELL_LNL) x[c] = n[c] * w.in[row[c]];
-        n[c] *= w.pt[row[c]];
-        sum += n[c];
+        st.n[c] = 0.0;
+        st.row[c] = kLongWin + lane;                    // this lane's dummy word
+        if (c < 2 || c < nch) { st.row[c] = __ldg(wp + 32 * c); st.n[c] = ell_ld_stream(qp + 32 * c); }
     }
-    sum = warp_sum(sum);
+    st.sum = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (MODE == ELL_LNL) st.x[c] = st.n[c] * w.in[st.row[c]];
+        st.n[c] *= w.pt[st.row[c]];
+        st.sum += st.n[c];
+    }
+}
+
+// phase 2 (st.sum already reduced over the warp): the read's contribution
+template <int MODE, int NC>
+__device__ __forceinline__ void ell_long_p2(EllLongState<MODE, NC>& st, const unsigned char* __restrict__ rec, int nch, int lane,
+                                            const EllLongWin w, const LogTab* s_log, double& lnl_local, const EllReassign& re,
+                                            const int* rowid) {
     if (MODE == ELL_FUSED) {
         const double wy = __ldg(reinterpret_cast<const double*>(rec));
-        const double g = (wy != 0.0) ? wy * recip0(sum) : 0.0;
+        const double g = (wy != 0.0) ? wy * recip0(st.sum) : 0.0;
         // loci are unique within a read and every empty slot has its own dummy word: plain read-modify-write
 #pragma unroll
-        for (int c = 0; c < NC; ++c) n[c] = w.acc[row[c]] + n[c] * g;
+        for (int c = 0; c < NC; ++c) st.n[c] = w.acc[st.row[c]] + st.n[c] * g;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) w.acc[row[c]] = n[c];
+        for (int c = 0; c < NC; ++c) w.acc[st.row[c]] = st.n[c];
     } else if (MODE == ELL_REASSIGN) {
-        const double rr = recip0(sum);
+        const double rr = recip0(st.sum);
         double zmax = 0.0, kept = 0.0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { n[c] *= rr; zmax = fmax(zmax, n[c]); if (n[c] >= re.thresh) kept += n[c]; }
+        for (int c = 0; c < NC; ++c) { st.n[c] *= rr; zmax = fmax(zmax, st.n[c]); if (st.n[c] >= re.thresh) kept += st.n[c]; }
         zmax = warp_max(zmax);
         kept = warp_sum(kept);
         int nb = 0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) nb += (n[c] == zmax && n[c] != 0.0);
+        for (int c = 0; c < NC; ++c) nb += (st.n[c] == zmax && st.n[c] != 0.0);
         nb = warp_sum_int(nb);
-        if (re.nbest && lane == 0 && re.rowid_slice[0] >= 0) re.nbest[re.rowid_slice[0]] = nb;
+        if (re.nbest && lane == 0 && rowid[0] >= 0) re.nbest[rowid[0]] = nb;
         if (re.want_colsum) {
             const double rk = recip0(kept);
 #pragma unroll
-            for (int c = 0; c < NC; ++c) n[c] = w.acc[row[c]] + ell_reassign_value(re.method, n[c], zmax, nb, re.thresh, rk);
+            for (int c = 0; c < NC; ++c) st.n[c] = w.acc[st.row[c]] + ell_reassign_value(re.method, st.n[c], zmax, nb, re.thresh, rk);
 #pragma unroll
-            for (int c = 0; c < NC; ++c) w.acc[row[c]] = n[c];
+            for (int c = 0; c < NC; ++c) w.acc[st.row[c]] = st.n[c];
         }
     } else {
-        const double rr = recip0(sum);
+        const double rr = recip0(st.sum);
         double acc2[2] = {0.0, 0.0};
         bool slow = false;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            const double xt = x[MODE == ELL_LNL ? c : 0];
-            n[c] *= rr;
-            const double term = n[c] * log_big_core(xt, s_log);
-            const bool use = n[c] != 0.0, ok = log_big_ok(xt);
+            const double xt = st.x[MODE == ELL_LNL ? c : 0];
+            st.n[c] *= rr;
+            const double term = st.n[c] * log_big_core(xt, s_log);
+            const bool use = st.n[c] != 0.0, ok = log_big_ok(xt);
             acc2[c & 1] += (use && ok) ? term : 0.0;
             slow = slow || (use && !ok);
         }
         lnl_local += acc2[0] + acc2[1];
         if (__any_sync(0xffffffffu, slow)) {
+            const unsigned short* wp = reinterpret_cast<const unsigned short*>(rec + 16) + lane;
+            const double* qp = reinterpret_cast<const double*>(rec + 16 + 64 * nch) + lane;
 #pragma unroll 1
             for (int c = 0; c < nch; ++c) {             // rare: recomputed from the record, library log1p
                 const unsigned r2 = wp[32 * c];
@@ -643,10 +659,34 @@ __device__ __forceinline__ void ell_long(const unsigned char* __restrict__ rec, 
     }
 }
 
+template <int MODE, int NC>
+__device__ __forceinline__ void ell_long(const unsigned char* __restrict__ rec, int nch, int lane, const EllLongWin w,
+                                         const LogTab* s_log, double& lnl_local, const EllReassign re, const int* rowid) {
+    EllLongState<MODE, NC> st;
+    ell_long_p1<MODE, NC>(st, rec, nch, lane, w);
+    st.sum = warp_sum(st.sum);
+    ell_long_p2<MODE, NC>(st, rec, nch, lane, w, s_log, lnl_local, re, rowid);
+}
+
+// two reads at once (both at most NC chunks, both inside the window)
+template <int MODE, int NC>
+__device__ __forceinline__ void ell_long2(const unsigned char* __restrict__ recA, int nchA, const unsigned char* __restrict__ recB,
+                                          int nchB, int lane, const EllLongWin w, const LogTab* s_log, double& lnl_local,
+                                          const EllReassign re, const int* rowidA) {
+    EllLongState<MODE, NC> A, B;
+    ell_long_p1<MODE, NC>(A, recA, nchA, lane, w);
+    ell_long_p1<MODE, NC>(B, recB, nchB, lane, w);
+    A.sum = warp_sum(A.sum);
+    B.sum = warp_sum(B.sum);
+    ell_long_p2<MODE, NC>(A, recA, nchA, lane, w, s_log, lnl_local, re, rowidA);
+    if (MODE != ELL_LNL) __syncwarp();               // B may touch the window words A just wrote, from other lanes
+    ell_long_p2<MODE, NC>(B, recB, nchB, lane, w, s_log, lnl_local, re, rowidA + 1);
+}
+
 // more than kLongRegs chunks (reads above 256 entries): the record is walked once per reduction (L2 hits)
 template <int MODE>
-__device__ __noinline__ void ell_long_big(const unsigned char* __restrict__ rec, int nch, int lane, const EllLongWin& w,
-                                          const LogTab* s_log, double& lnl_local, const EllReassign& re) {
+__device__ __noinline__ void ell_long_big(const unsigned char* __restrict__ rec, int nch, int lane, const EllLongWin w,
+                                          const LogTab* s_log, double& lnl_local, const EllReassign re, const int* rowid) {
     const unsigned short* wp = reinterpret_cast<const unsigned short*>(rec + 16) + lane;
     const double* qp = reinterpret_cast<const double*>(rec + 16 + 64 * nch) + lane;
     double sum = 0.0;
@@ -675,7 +715,7 @@ __device__ __noinline__ void ell_long_big(const unsigned char* __restrict__ rec,
         int nb = 0;
         for (int c = 0; c < nch; ++c) { const double z = (qp[32 * c] * w.pt[wp[32 * c]]) * rr; nb += (z == zmax && z != 0.0); }
         nb = warp_sum_int(nb);
-        if (re.nbest && lane == 0 && re.rowid_slice[0] >= 0) re.nbest[re.rowid_slice[0]] = nb;
+        if (re.nbest && lane == 0 && rowid[0] >= 0) re.nbest[rowid[0]] = nb;
         if (re.want_colsum) {
             const double rk = recip0(kept);
             for (int c = 0; c < nch; ++c) {
@@ -821,7 +861,12 @@ __global__ void __launch_bounds__(32) k_ell_long(const EllArgs a) {
     double* l_in = l_pt + kLongWin + 32;
     LogTab* s_log = reinterpret_cast<LogTab*>(l_acc + kLongDoubles);
     const int lane = threadIdx.x;
-    const long long r_begin = a.range[blockIdx.x], r_end = a.range[blockIdx.x + 1];     // this warp's run of long reads
+    // Work split: batches of 32 consecutive records, dealt round-robin to the warps -- at any moment the resident warps
+    // read neighbouring batches, i.e. a few pages of the stream (a contiguous run per warp would keep ~3000 distant pages
+    // live at once; with ~1.5 KB per record that costs a TLB miss per read).  The stream is sorted by first locus, so a
+    // warp's consecutive batches still move forward through the loci.
+    const long long r_end = a.n_slices;                       // (here: the number of long-read records)
+    const long long b_step = (long long)gridDim.x * 32;
     const int K = a.K;
     const double* __restrict__ pt = a.pt;
     const unsigned char* __restrict__ stream = a.stream;
@@ -853,12 +898,13 @@ __global__ void __launch_bounds__(32) k_ell_long(const EllArgs a) {
         if (my && j < K && s != 0.0) atomicAdd(my + j, s);
     };
 
-    int4 cur = load_batch(r_begin), nxt = load_batch(r_begin + 32);
+    const long long b_first = (long long)blockIdx.x * 32;
+    int4 cur = load_batch(b_first), nxt = load_batch(b_first + b_step);
     if (lane < kEllAhead) prefetch_mine(cur);
     int Fb = -1;                                      // first block (32 loci) of the window; -1 = empty
 
-    for (long long b = r_begin; b < r_end; b += 32) {
-        const int4 after = load_batch(b + 64);
+    for (long long b = b_first; b < r_end; b += b_step) {
+        const int4 after = load_batch(b + 2 * b_step);
         const int nrec = (int)min(32LL, r_end - b);
         for (int c = 0; c < nrec; ++c) {
             {
@@ -890,13 +936,35 @@ __global__ void __launch_bounds__(32) k_ell_long(const EllArgs a) {
                 Fb = lb;
                 __syncwarp();
             }
-            if (MODE == ELL_REASSIGN) re.rowid_slice = a.rowid + (b + c);
+            const int* rowid = (MODE == ELL_REASSIGN) ? a.rowid + (b + c) : nullptr;
+            // ---- the next read of the batch goes along when it fits the registers and the window as it stands
+            if (nch <= kLongRegs && c + 1 < nrec) {
+                const int thi2 = __shfl_sync(0xffffffffu, cur.z, c + 1);
+                const int nch2 = thi2 & 0x7f;
+                if (nch2 <= kLongRegs && ((thi2 >> 8) >> 5) < Fb + kBlocks) {
+                    const unsigned off2 = (unsigned)__shfl_sync(0xffffffffu, cur.x, c + 1);
+                    const unsigned char* rec2 = stream + ((long long)off2 << 4);
+                    {
+                        const int pc = c + 1 + kEllAhead;
+                        if (lane == (pc & 31)) prefetch_mine(pc < 32 ? cur : nxt);
+                    }
+                    switch ((max(nch, nch2) + 1) >> 1) {
+                        case 1: ell_long2<MODE, 2>(rec, nch, rec2, nch2, lane, lw, s_log, lnl_local, re, rowid); break;
+                        case 2: ell_long2<MODE, 4>(rec, nch, rec2, nch2, lane, lw, s_log, lnl_local, re, rowid); break;
+                        case 3: ell_long2<MODE, 6>(rec, nch, rec2, nch2, lane, lw, s_log, lnl_local, re, rowid); break;
+                        default: ell_long2<MODE, 8>(rec, nch, rec2, nch2, lane, lw, s_log, lnl_local, re, rowid); break;
+                    }
+                    __syncwarp();
+                    ++c;
+                    continue;
+                }
+            }
             switch ((nch + 1) >> 1) {
-                case 1: ell_long<MODE, 2>(rec, nch, lane, lw, s_log, lnl_local, re); break;
-                case 2: ell_long<MODE, 4>(rec, nch, lane, lw, s_log, lnl_local, re); break;
-                case 3: ell_long<MODE, 6>(rec, nch, lane, lw, s_log, lnl_local, re); break;
-                case 4: ell_long<MODE, 8>(rec, nch, lane, lw, s_log, lnl_local, re); break;
-                default: ell_long_big<MODE>(rec, nch, lane, lw, s_log, lnl_local, re); break;
+                case 1: ell_long<MODE, 2>(rec, nch, lane, lw, s_log, lnl_local, re, rowid); break;
+                case 2: ell_long<MODE, 4>(rec, nch, lane, lw, s_log, lnl_local, re, rowid); break;
+                case 3: ell_long<MODE, 6>(rec, nch, lane, lw, s_log, lnl_local, re, rowid); break;
+                case 4: ell_long<MODE, 8>(rec, nch, lane, lw, s_log, lnl_local, re, rowid); break;
+                default: ell_long_big<MODE>(rec, nch, lane, lw, s_log, lnl_local, re, rowid); break;
             }
             __syncwarp();          // the next read touches the same window words from other lanes
         }

@@ -499,7 +499,7 @@ def test_small_scores_take_the_library_log1p(kernel):
 
 def test_ell_long_read_records(monkeypatch):
     """Reads of more than 48 entries live in the stream as one record each (csrc/tsc_ell.cuh, long mode): 49 entries (two
-    chunks), 256 / 257 (registers / walked), locus spans of 992 (fits the 1024-locus window) and 993 (residual), dense
+    chunks), 256 / 257 (registers / walked), locus spans of 480 (fits the 512-locus window) and 481 (residual), dense
     groups and isolated first loci (window advances inside long mode), mixed with short reads so that a warp's run crosses
     the slice -> long-read boundary.  EM, log-likelihood, every reassign mode and the best-hit counts against the oracle."""
     monkeypatch.setenv("TELESCOPE_B200_LONG_RECORDS", "1")
@@ -514,11 +514,11 @@ def test_ell_long_read_records(monkeypatch):
     for first in (0, 7, 500, 501, 1900):
         for _ in range(30):
             n = int(rng.integers(49, 300))
-            rows.append(run(first, n, int(rng.integers(n - 1, 993))))
-    rows.append(run(3, 49, 48)); rows.append(run(3, 49, 992)); rows.append(run(3, 49, 993))
-    rows.append(run(11, 256, 700)); rows.append(run(11, 257, 700)); rows.append(run(11, 993, 992))
+            rows.append(run(first, n, int(rng.integers(n - 1, 481))))
+    rows.append(run(3, 49, 48)); rows.append(run(3, 49, 480)); rows.append(run(3, 49, 481))
+    rows.append(run(11, 256, 400)); rows.append(run(11, 257, 400)); rows.append(run(11, 481, 480)); rows.append(run(11, 300, 900))
     for first in range(100, K - 1000, 211):
-        rows.append(run(first, int(rng.integers(49, 120)), int(rng.integers(200, 993))))
+        rows.append(run(first, int(rng.integers(49, 120)), int(rng.integers(200, 481))))
     for _ in range(600):                                        # short reads around the same loci
         f = int(rng.integers(0, K - 100)); n = int(rng.integers(1, 40))
         rows.append(np.array([f]) if n == 1 else run(f, n, int(rng.integers(n - 1, 97))))

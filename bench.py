@@ -362,8 +362,16 @@ def main():
         t = max_over_ranks(time.perf_counter() - t0)
         return tl, t, t_create
 
-    tl, t_e2e, t_create = timed_e2e(m, "e2e")
-    create_s, create_laps = tl.create_seconds, tl.create_laps
+    # three whole jobs back to back (each: fresh model from the host arrays, K iterations, parameters to the host); the
+    # line reports the median run and lists all three
+    e2e_runs = []
+    for rep in range(3):
+        tl, t_e2e, t_create = timed_e2e(m, "e2e%d" % rep)
+        e2e_runs.append((t_e2e, t_create, tl.create_seconds, tl.create_laps))
+        if rep < 2:
+            live["tl"] = None
+            tl.close()
+    t_e2e, t_create, create_s, create_laps = sorted(e2e_runs)[1]
     assert int(max_over_ranks(float(m.data.max()))) == max_score, "score range assumption violated"
     total_nnz = int(sum_over_ranks(float(local_nnz)))
     c_e2e = tl.counters()
@@ -436,6 +444,11 @@ def main():
                         "construction %.3f s; the library was warmed up once on a 4096-read toy matrix before the timer "
                         "(CUDA module load), nothing of the workload is cached" % (K, t_create),
                 "construction_s": t_create, "tsc_create_s": create_s, "tsc_create_laps_ms": create_laps,
+                "runs": [K / r[0] for r in e2e_runs],
+                "runs_what": "three whole jobs back to back in this process, value = the median run; the first one allocates its "
+                             "device memory from the driver, the later ones get the blocks the destroyed model handed back to "
+                             "the library's cache (no data is cached: every job uploads and rebuilds everything)",
+                "runs_laps_ms": [r[3] for r in e2e_runs],
             },
             "e2e_report": {
                 "value": K / (t_e2e + t_report), "unit": UNIT, "report_s": t_report,

@@ -107,6 +107,11 @@ void tsc_config_default(tsc_config* cfg);
 /* page-locked host memory for the CSR arrays (optional; uploads from it run at full PCIe speed) */
 void* tsc_pinned_alloc(uint64_t bytes);
 void tsc_pinned_free(void* p);
+/* Device blocks of destroyed models are kept for the next model of this process (cudaMalloc / cudaFree of tens of
+ * gigabytes cost more than the upload they precede); this hands them back to the driver.  The cache is bounded by
+ * TELESCOPE_B200_CACHE_GB (default 96, 0 = off) and emptied on its own when an allocation fails.  No counterpart in the
+ * reference (numpy frees on garbage collection). */
+void tsc_trim_memory(void);
 
 /*
  * TelescopeLikelihood.__init__ (model.py:635-700).

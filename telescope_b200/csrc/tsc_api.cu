@@ -26,6 +26,8 @@
 #include <numeric>
 #include <string>
 #include <thread>
+#include <map>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -102,11 +104,135 @@ static int nccl_load() {
                                           std::to_string(__LINE__) + ")");                            \
     } while (0)
 
+// ------------------------------------------------------------------------------------------------- device memory
+// cudaMalloc / cudaFree of large blocks cost milliseconds each -- sometimes tens of milliseconds while copies are in
+// flight -- and cudaFree synchronises the device.  A model allocates ~15 blocks; a process that builds models one after
+// the other (the CLI's assign + resume, a service, the benchmark's repeated jobs) would pay that every time.  So blocks
+// go back to a process-wide cache when a model is destroyed and are handed out again to a request of
+// (nearly) the same size on the same device (model after model on similar data asks for the same sizes).  The cache is
+// bounded (TELESCOPE_B200_CACHE_GB, default 96; 0 switches it off), emptied by tsc_trim_memory() and whenever an
+// allocation fails.  Pinned host words of the loop state come from a small pool that is never returned.
+struct DevCache {
+    std::mutex mu;
+    std::unordered_map<void*, std::pair<int, size_t>> live;                 // handed out: device, bytes
+    std::multimap<std::pair<int, size_t>, void*> idle;                      // (device, bytes) -> block
+    size_t idle_bytes = 0;
+    std::vector<void*> pinned_words;                                        // 256-byte pinned host slots, reusable
+    double ms = 0.0;                                                        // time spent in the driver's allocation calls
+    long long calls = 0, hits = 0;
+    size_t limit() const {
+        const char* e = getenv("TELESCOPE_B200_CACHE_GB");
+        const double gb = e ? atof(e) : 96.0;
+        return gb <= 0 ? 0 : (size_t)(gb * (double)(1ULL << 30));
+    }
+    void trim_locked(size_t keep) {
+        while (idle_bytes > keep && !idle.empty()) {
+            auto it = std::prev(idle.end());                                // largest block of the highest device first
+            int cur = 0;
+            cudaGetDevice(&cur);
+            cudaSetDevice(it->first.first);
+            cudaFree(it->second);
+            cudaSetDevice(cur);
+            idle_bytes -= it->first.second;
+            idle.erase(it);
+        }
+    }
+};
+static DevCache g_cache;
+constexpr size_t kCacheMinBytes = 1;          // every block: even a 4-byte cudaMalloc / cudaFree pair is a device synchronisation
+
+static cudaError_t dev_malloc_bytes(void** out, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bytes >= kCacheMinBytes) {
+        std::lock_guard<std::mutex> g(g_cache.mu);
+        // best fit: the smallest idle block of this device that is large enough and at most 1/8 (or 64 KB) larger -- a few
+        // sizes of a model depend on the order in which atomics happened to append reads and differ by a little
+        auto it = g_cache.idle.lower_bound({dev, bytes});
+        if (it != g_cache.idle.end() && it->first.first == dev && it->first.second <= bytes + std::max<size_t>(bytes / 8, 65536)) {
+            const size_t got = it->first.second;
+            *out = it->second;
+            g_cache.idle_bytes -= got;
+            g_cache.idle.erase(it);
+            g_cache.live[*out] = {dev, got};
+            ++g_cache.hits;
+            return cudaSuccess;
+        }
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {           // make room: everything idle goes back to the driver, once
+        cudaGetLastError();
+        { std::lock_guard<std::mutex> g(g_cache.mu); g_cache.trim_locked(0); }
+        e = cudaMalloc(out, bytes);
+    }
+    std::lock_guard<std::mutex> g(g_cache.mu);
+    g_cache.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ++g_cache.calls;
+    if (e == cudaSuccess && bytes >= kCacheMinBytes) g_cache.live[*out] = {dev, bytes};
+    return e;
+}
+template <typename T> static cudaError_t dev_malloc(T** out, size_t bytes) { return dev_malloc_bytes((void**)out, bytes); }
+
+// Like cudaFree, this waits for the device first: nobody may still be using the block when its next owner gets it.
+static void dev_free(void* p) {
+    if (!p) return;
+    std::unique_lock<std::mutex> g(g_cache.mu);
+    auto it = g_cache.live.find(p);
+    if (it == g_cache.live.end()) {
+        g.unlock();
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaFree(p);
+        g.lock();
+        g_cache.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        ++g_cache.calls;
+        return;
+    }
+    const std::pair<int, size_t> key = it->second;
+    g_cache.live.erase(it);
+    const size_t lim = g_cache.limit();
+    if (lim == 0 || key.second > lim) { g.unlock(); cudaFree(p); return; }
+    g.unlock();
+    {   // the block's last user may still be running
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != key.first) cudaSetDevice(key.first);
+        cudaDeviceSynchronize();
+        if (cur != key.first) cudaSetDevice(cur);
+    }
+    g.lock();
+    g_cache.idle.insert({key, p});
+    g_cache.idle_bytes += key.second;
+    if (g_cache.idle_bytes > lim) g_cache.trim_locked(lim);
+}
+
+static void* pinned_word_take() {
+    {
+        std::lock_guard<std::mutex> g(g_cache.mu);
+        if (!g_cache.pinned_words.empty()) { void* p = g_cache.pinned_words.back(); g_cache.pinned_words.pop_back(); return p; }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, 256, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+static void pinned_word_give(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(g_cache.mu);
+    g_cache.pinned_words.push_back(p);
+}
+
+extern "C" void tsc_trim_memory(void) {
+    std::lock_guard<std::mutex> g(g_cache.mu);
+    g_cache.trim_locked(0);
+}
+
 // ------------------------------------------------------------------------------------------------- handle
 struct Shard {
     int dev = 0;
     int world_rank = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux = nullptr;        // construction: the per-chunk kernels that run beside the upload of the next chunk
+    cudaEvent_t ev_up = nullptr;
     long long n_rows = 0, nnz = 0;
     long long row_begin = 0, nnz_begin = 0;   // within this process's (compacted) reads / entries
     long long* indptr = nullptr;
@@ -162,6 +288,10 @@ struct Shard {
     int4* ell_index = nullptr;            // per slice record: offset / 16, first locus, T | last locus << 8, reads
     int ell_grid = 0, ell_grid_lnl = 0;
     long long *ell_range = nullptr, *ell_range_lnl = nullptr;      // record boundaries of the CTAs (grid + 1 each)
+    unsigned* ell_cta_ns = nullptr;       // per CTA of the per-iteration kernel: duration of its last measured launch
+    double* ell_rebal = nullptr;          // scratch of k_ell_rebalance, 2 * (grid + 1)
+    int ell_rebal_left = 0;               // measured re-partitions still to do (the first iterations of the model)
+    long long ell_slice_bytes = 0;        // bytes of the slice records (the long-read records follow them in the stream)
     long long *ell_lrange = nullptr, *ell_lrange_lnl = nullptr;    // the same for the long-read kernel
     int ell_lgrid = 0, ell_lgrid_lnl = 0;
     int* ell_rowid = nullptr;             // 16 per slice: the shard's read in each slot (-1 = empty)
@@ -408,21 +538,24 @@ extern "C" void tsc_config_default(tsc_config* cfg) {
 static void free_shard(Shard& s) {
     cudaSetDevice(s.dev);
     if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.aux) cudaStreamSynchronize(s.aux);
     void* ptrs[] = {s.indptr, s.col, s.q, s.wy, s.tiles, s.pi, s.theta, s.pt, s.pi_prev, s.theta_prev, s.pt_prev,
                     s.pi_init, s.theta_init, s.pisum0, s.acc, s.thetasum, s.ones, s.tmp_a, s.tmp_b, s.tmp_c, s.colsum,
                     s.perm, s.rep, s.consts, s.st, s.diffs, s.lnls, s.partials, s.scalars, s.bad,
-                    s.ell_stream, s.ell_index, s.ell_range, s.ell_range_lnl, s.ell_lrange, s.ell_lrange_lnl, s.ell_rowid, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles, s.res_tiles_amb,
+                    s.ell_stream, s.ell_index, s.ell_range, s.ell_range_lnl, s.ell_cta_ns, s.ell_rebal, s.ell_lrange, s.ell_lrange_lnl, s.ell_rowid, s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_tiles, s.res_tiles_amb,
                     s.peer_ptrs_d, s.tail_partials, s.tail_ticket, s.peer_err, s.log_tab};
-    for (void* p : ptrs) if (p && !s.in_slab(p)) cudaFree(p);
-    for (auto& b : s.slabs) cudaFree(b.first);
+    for (void* p : ptrs) if (p && !s.in_slab(p)) dev_free(p);
+    for (auto& b : s.slabs) dev_free(b.first);
     for (size_t r = 0; r < s.peer_map.size(); ++r)
         if (r < s.peer_opened.size() && s.peer_opened[r] && s.peer_map[r]) cudaIpcCloseMemHandle(s.peer_map[r]);
-    if (s.peer_own) cudaFree(s.peer_own);
-    if (s.st_host) cudaFreeHost(s.st_host);
+    if (s.peer_own) dev_free(s.peer_own);      // (a block shared through IPC is not in the cache: plain cudaFree)
+    pinned_word_give(s.st_host);
     for (auto& e : s.ev_poll) if (e) cudaEventDestroy(e);
     for (auto& e : s.ev_k) if (e) cudaEventDestroy(e);
     for (auto& e : s.ev_em) if (e) cudaEventDestroy(e);
     if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
+    if (s.ev_up) cudaEventDestroy(s.ev_up);
+    if (s.aux) cudaStreamDestroy(s.aux);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Shard();
 }
@@ -442,12 +575,13 @@ static void peer_geometry(int K, int* kpad, int* nb, int* cap) {
     *cap = *kpad + 64;          // larger reductions go through the inbox in pieces
 }
 
-static int peer_buffer_alloc(int dev, int K, int world, unsigned char** out) {
+static int peer_buffer_alloc(int dev, int K, int world, unsigned char** out, bool ipc) {
     int kpad, nb, cap;
     peer_geometry(K, &kpad, &nb, &cap);
     const size_t bytes = 8 * peer_buffer_words(world, kpad, nb, cap);
     CU(cudaSetDevice(dev));
-    CU(cudaMalloc(out, bytes));
+    if (ipc) CU(cudaMalloc(out, bytes));         // other processes map it: a block of its own, returned to the driver
+    else CU(dev_malloc(out, bytes));
     CU(cudaMemset(*out, 0, bytes));            // flags start at epoch 0, before anybody can map the buffer
     CU(cudaDeviceSynchronize());
     return TSC_OK;
@@ -456,7 +590,7 @@ static int peer_buffer_alloc(int dev, int K, int world, unsigned char** out) {
 extern "C" int tsc_peer_buffer_create(int32_t device, int32_t n_cols, int32_t world, void** buf_out, void* ipc_handle64_out) {
     if (!buf_out || !ipc_handle64_out || n_cols <= 0 || world <= 0) return fail(TSC_ERR_ARG, "bad argument");
     unsigned char* buf = nullptr;
-    int rc = peer_buffer_alloc(device, n_cols, world, &buf);
+    int rc = peer_buffer_alloc(device, n_cols, world, &buf, true);
     if (rc) return rc;
     cudaIpcMemHandle_t hd;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
@@ -517,7 +651,7 @@ static int setup_transport(tsc_handle* h, const tsc_config& cfg) {
             s.peer_map.assign(h->world, nullptr);
             s.peer_opened.assign(h->world, 0);
             if (h->n_procs > 1) s.peer_own = (unsigned char*)cfg.peer_buffer;           // ownership moves to the handle
-            else { int rc = peer_buffer_alloc(s.dev, h->K, h->world, &s.peer_own); if (rc) return rc; }
+            else { int rc = peer_buffer_alloc(s.dev, h->K, h->world, &s.peer_own, false); if (rc) return rc; }
             s.peer_map[s.world_rank] = s.peer_own;
         }
         if (h->n_procs > 1) {
@@ -525,7 +659,7 @@ static int setup_transport(tsc_handle* h, const tsc_config& cfg) {
             {
                 Shard& s0 = h->shards[0];
                 CU(cudaSetDevice(s0.dev));
-                CU(cudaMalloc(&s0.peer_ptrs_d, sizeof(unsigned char*) * h->world));
+                CU(dev_malloc(&s0.peer_ptrs_d, sizeof(unsigned char*) * h->world));
             }
             std::vector<char> handles((const char*)cfg.peer_handles, (const char*)cfg.peer_handles + 64 * (size_t)h->world);
             h->peer_thread = std::thread([h, handles]() {
@@ -566,13 +700,13 @@ static int setup_transport(tsc_handle* h, const tsc_config& cfg) {
         for (auto& s : h->shards) {
             CU(cudaSetDevice(s.dev));
             if (h->n_procs == 1) {
-                CU(cudaMalloc(&s.peer_ptrs_d, sizeof(unsigned char*) * h->world));
+                CU(dev_malloc(&s.peer_ptrs_d, sizeof(unsigned char*) * h->world));
                 CU(cudaMemcpy(s.peer_ptrs_d, s.peer_map.data(), sizeof(unsigned char*) * h->world, cudaMemcpyHostToDevice));
             }
-            CU(cudaMalloc(&s.tail_partials, sizeof(double) * h->nb_tail));
-            CU(cudaMalloc(&s.tail_ticket, sizeof(unsigned)));
+            CU(dev_malloc(&s.tail_partials, sizeof(double) * h->nb_tail));
+            CU(dev_malloc(&s.tail_ticket, sizeof(unsigned)));
             CU(cudaMemset(s.tail_ticket, 0, sizeof(unsigned)));
-            CU(cudaMalloc(&s.peer_err, sizeof(int)));
+            CU(dev_malloc(&s.peer_err, sizeof(int)));
             CU(cudaMemset(s.peer_err, 0, sizeof(int)));
         }
     }
@@ -614,7 +748,7 @@ static int upload(tsc_handle* h, Shard& s, void* dst, const void* src, size_t by
     if (bytes == 0) return TSC_OK;
     h->h2d += (long long)bytes;
     int threads = (int)std::thread::hardware_concurrency() / std::max(1, h->n_procs * (int)h->shards.size());
-    threads = std::max(1, std::min(threads, 8));
+    threads = std::max(1, std::min(threads - 2, 12));          // (two cores stay free for this thread and the driver's)
     if (bytes < (32u << 20) || host_is_pinned(src) || getenv("TELESCOPE_B200_NO_STAGING")) {
         CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.stream));
         return TSC_OK;
@@ -731,12 +865,12 @@ struct DevBuf {              // device temporaries released on every exit path
     std::vector<void*> p;
     Arena* arena = nullptr;  // tried first; cudaMalloc only when it is full (every cudaMalloc/cudaFree of a large
                              // block costs milliseconds and a device synchronisation)
-    ~DevBuf() { for (void* q : p) if (q) cudaFree(q); }
+    ~DevBuf() { for (void* q : p) if (q) dev_free(q); }
     template <typename T> cudaError_t alloc(T** out, size_t n) {
         const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
         if (arena) { void* q = arena->take(bytes); if (q) { *out = (T*)q; return cudaSuccess; } }
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, bytes);
+        cudaError_t e = dev_malloc(&q, bytes);
         *out = (T*)q;
         if (e == cudaSuccess) p.push_back(q);
         return e;
@@ -756,7 +890,7 @@ struct SlabPlan {            // sizes first, one cudaMalloc, then the pointers
         size_t total = 0;
         for (auto& it : items) total += (it.bytes + 255) & ~(size_t)255;
         char* base = nullptr;
-        CU(cudaMalloc(&base, std::max<size_t>(total, 256)));
+        CU(dev_malloc(&base, std::max<size_t>(total, 256)));
         s.slabs.push_back({base, std::max<size_t>(total, 256)});
         size_t off = 0;
         for (auto& it : items) { *it.out = base + off; off += (it.bytes + 255) & ~(size_t)255; }
@@ -765,7 +899,8 @@ struct SlabPlan {            // sizes first, one cudaMalloc, then the pointers
 };
 
 static int build_tiles(tsc_handle* h, Shard& s, const long long* indptr_d, long long n_rows, Tile** tiles_out,
-                       long long* n_tiles_out, long long* n_long_out, Arena* arena = nullptr) {
+                       long long* n_tiles_out, long long* n_long_out, Arena* arena = nullptr, cudaStream_t st = nullptr) {
+    if (!st) st = s.stream;
     const int n_chunks = (int)((n_rows + kChunkRows - 1) / kChunkRows);
     DevBuf tmp;
     tmp.arena = arena;
@@ -777,29 +912,29 @@ static int build_tiles(tsc_handle* h, Shard& s, const long long* indptr_d, long 
     CU(tmp.alloc(&counts_d, n_chunks));
     CU(tmp.alloc(&offs_d, n_chunks));
     CU(tmp.alloc(&nlong_d, 1));
-    CU(cudaMemsetAsync(nlong_d, 0, sizeof(unsigned long long), s.stream));
+    CU(cudaMemsetAsync(nlong_d, 0, sizeof(unsigned long long), st));
     std::vector<int> counts(n_chunks);
     std::vector<long long> offs(n_chunks);
     if (n_chunks > 0) {
-        k_tile_count<<<(n_chunks + 127) / 128, 128, 0, s.stream>>>(indptr_d, n_rows, counts_d, n_chunks);
+        k_tile_count<<<(n_chunks + 127) / 128, 128, 0, st>>>(indptr_d, n_rows, counts_d, n_chunks);
         LAUNCH(h);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(counts.data(), counts_d, sizeof(int) * n_chunks, cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaStreamSynchronize(s.stream));
+        CU(cudaMemcpyAsync(counts.data(), counts_d, sizeof(int) * n_chunks, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
     }
     long long total = 0;
     for (int c = 0; c < n_chunks; ++c) { offs[c] = total; total += counts[c]; }
     *n_tiles_out = total;
-    CU(cudaMalloc(tiles_out, sizeof(Tile) * std::max<long long>(total, 1)));
+    CU(dev_malloc(tiles_out, sizeof(Tile) * std::max<long long>(total, 1)));
     if (n_chunks > 0) {
-        CU(cudaMemcpyAsync(offs_d, offs.data(), sizeof(long long) * n_chunks, cudaMemcpyHostToDevice, s.stream));
-        k_tile_fill<<<(n_chunks + 127) / 128, 128, 0, s.stream>>>(indptr_d, n_rows, offs_d, n_chunks, *tiles_out, nlong_d);
+        CU(cudaMemcpyAsync(offs_d, offs.data(), sizeof(long long) * n_chunks, cudaMemcpyHostToDevice, st));
+        k_tile_fill<<<(n_chunks + 127) / 128, 128, 0, st>>>(indptr_d, n_rows, offs_d, n_chunks, *tiles_out, nlong_d);
         LAUNCH(h);
         CU(cudaGetLastError());
     }
     unsigned long long nl = 0;
-    CU(cudaMemcpyAsync(&nl, nlong_d, sizeof(nl), cudaMemcpyDeviceToHost, s.stream));
-    CU(cudaStreamSynchronize(s.stream));
+    CU(cudaMemcpyAsync(&nl, nlong_d, sizeof(nl), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     *n_long_out = (long long)nl;
     if (arena) arena->off = mark.off;
     return TSC_OK;
@@ -883,7 +1018,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
             // kept: slot -> read of every slice, then the long reads (best-hit counts of reassign go back through it);
             // the short slots are padded to whole slices
             slots_short = ((n_short + kEllReads - 1) / kEllReads) * kEllReads;
-            CU(cudaMalloc(&s.ell_rowid, sizeof(int) * (slots_short + n_long)));
+            CU(dev_malloc(&s.ell_rowid, sizeof(int) * (slots_short + n_long)));
             CU(cudaMemsetAsync(s.ell_rowid, 0xff, sizeof(int) * (slots_short + n_long), s.stream));
             sorted = s.ell_rowid;
             k_ell_scatter<<<g, 256, 0, s.stream>>>(key, n_rows, bin_start, cursor, sorted, n_short_keys, n_stream_keys, slots_short - n_short);
@@ -895,7 +1030,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         const long long n_slices = slots_short / kEllReads, n_records = n_slices + n_long;
         int* rec_bytes = nullptr;
         long long* rec_off = nullptr;
-        CU(cudaMalloc(&s.ell_index, sizeof(int4) * n_records));      // kept: the kernels' record index
+        CU(dev_malloc(&s.ell_index, sizeof(int4) * n_records));      // kept: the kernels' record index
         CU(tmp.alloc(&rec_bytes, n_records));
         CU(tmp.alloc(&rec_off, (size_t)n_records + 1));
         lap("  ell scatter");
@@ -921,7 +1056,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         const int warps = s.n_sm * std::max(per_sm, 1);
         lap("  ell slices+scan");
         if (total >= (1LL << 36)) return fail(TSC_ERR_ARG, "slice stream of one GPU exceeds 64 GB");
-        CU(cudaMalloc(&s.ell_stream, (size_t)total));
+        CU(dev_malloc(&s.ell_stream, (size_t)total));
         lap("  ell stream malloc");
         if (n_slices > 0) {
             k_ell_fill<<<grid_for(n_slices * 32, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, s.col, s.q, s.wy, sorted, n_short, n_slices,
@@ -936,6 +1071,8 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         }
         CU(cudaGetLastError());
         s.ell_bytes = total;
+        s.ell_slice_bytes = total;
+        if (n_long > 0 && n_slices > 0 && (rc = fetch_ll(s, rec_off + n_slices, &s.ell_slice_bytes))) return rc;
         s.ell_slices = n_slices;
         s.ell_long = n_long;
         s.ell_records = n_records;
@@ -943,13 +1080,22 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         // slices and long reads have a kernel (and a split) each
         auto split = [&](const long long* off, long long n, int cap, int* grid, long long** range) -> int {
             *grid = (int)std::max<long long>(1, std::min<long long>((n + 7) / 8, cap));
-            CU(cudaMalloc(range, sizeof(long long) * (*grid + 1)));
+            CU(dev_malloc(range, sizeof(long long) * (*grid + 1)));
             k_ell_ranges<<<(*grid + 256) / 256, 256, 0, s.stream>>>(off, n, *grid, *range);
             LAUNCH(h);
             return TSC_OK;
         };
         if (n_slices > 0) {
             if ((rc = split(rec_off, n_slices, warps, &s.ell_grid, &s.ell_range))) return rc;
+            // the first iterations of the model measure how long every run takes and move the boundaries accordingly
+            const char* rb_env = getenv("TELESCOPE_B200_REBALANCE");
+            s.ell_rebal_left = rb_env ? atoi(rb_env) : 2;
+            if (s.ell_grid < 2 || s.ell_grid + 1 > 4096) s.ell_rebal_left = 0;
+            if (s.ell_rebal_left > 0) {
+                CU(dev_malloc(&s.ell_cta_ns, sizeof(unsigned) * s.ell_grid));
+                CU(dev_malloc(&s.ell_rebal, sizeof(double) * 2 * (s.ell_grid + 1)));
+                CU(cudaMemsetAsync(s.ell_cta_ns, 0, sizeof(unsigned) * s.ell_grid, s.stream));
+            }
             if ((rc = split(rec_off, n_slices, s.n_sm * std::max(per_sm_lnl, 1), &s.ell_grid_lnl, &s.ell_range_lnl))) return rc;
         }
         if (n_long > 0) {
@@ -1048,6 +1194,17 @@ static int create_impl(tsc_handle* h, const tsc_config& cfg, const CreateInput& 
         return fail(TSC_ERR_ARG, "indptr[0] must be 0 and indptr[n_rows] must be nnz");
 
     StageTimer tm(&h->create_laps);
+    struct AllocStats {          // what this construction spent in the driver's allocation calls, appended to the laps
+        std::string* log; double ms0; long long calls0, hits0;
+        ~AllocStats() {
+            std::lock_guard<std::mutex> g(g_cache.mu);
+            char buf[128];
+            snprintf(buf, sizeof buf, "driver alloc calls=%lld (%.1f ms), cache hits=%lld;", g_cache.calls - calls0, g_cache.ms - ms0,
+                     g_cache.hits - hits0);
+            *log += buf;
+        }
+    } alloc_stats{&h->create_laps, 0.0, 0, 0};
+    { std::lock_guard<std::mutex> g(g_cache.mu); alloc_stats.ms0 = g_cache.ms; alloc_stats.calls0 = g_cache.calls; alloc_stats.hits0 = g_cache.hits; }
     // Fast path: the caller's read pointers are used as they are (validated and rebased on the device).  Matrices
     // with empty reads take the slow path: tiny ones are checked here, large ones are detected on the device and the
     // attempt is repeated once with the reads compacted on the host (streams and communicators are kept).
@@ -1104,6 +1261,8 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         if (s.n_rows >= (1LL << 31)) return fail(TSC_ERR_ARG, "more than 2^31 reads on one GPU");
         CU(cudaSetDevice(s.dev));
         if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        if (!s.aux) CU(cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
+        if (!s.ev_up) CU(cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming));
         CU(cudaDeviceGetAttribute(&s.n_sm, cudaDevAttrMultiProcessorCount, s.dev));
     }
     if (!h->shards[0].peer_own && !h->shards[0].comm) {
@@ -1174,7 +1333,9 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             const size_t ib = slow ? sizeof(long long) : (size_t)indptr_bytes;
             DevBuf ipbuf;
             char* ip_native = nullptr;
-            CU(ipbuf.alloc(&ip_native, ib * (s.n_rows + 1)));
+            // (the Q array is not written before the read pointers are through: it lends its memory, no allocation call)
+            if (ib * (size_t)(s.n_rows + 1) <= sizeof(double) * (size_t)s.nnz) ip_native = (char*)s.q;
+            else CU(ipbuf.alloc(&ip_native, ib * (s.n_rows + 1)));
             const char* src = slow ? (const char*)(ip_compact->data() + s.row_begin) : (const char*)indptr + ib * s.row_begin;
             { int rc = upload(h, s, ip_native, src, ib * (s.n_rows + 1)); if (rc) return rc; }
             const int g = grid_for(s.n_rows + 1, 256, s.n_sm * 16);
@@ -1190,8 +1351,8 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
                 for (auto& sh : h->shards) {        // release this attempt's slabs; streams and the transport stay
                     cudaSetDevice(sh.dev);
                     if (sh.stream) cudaStreamSynchronize(sh.stream);
-                    if (sh.tiles && !sh.in_slab(sh.tiles)) cudaFree(sh.tiles);
-                    for (auto& b : sh.slabs) cudaFree(b.first);
+                    if (sh.tiles && !sh.in_slab(sh.tiles)) dev_free(sh.tiles);
+                    for (auto& b : sh.slabs) dev_free(b.first);
                     sh.slabs.clear();
                     sh.indptr = nullptr; sh.col = nullptr; sh.q = nullptr; sh.wy = nullptr; sh.bad = nullptr; sh.tiles = nullptr;
                     sh.raw = nullptr;
@@ -1206,20 +1367,60 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             CU(cudaMemsetAsync(s.bad, 0, sizeof(int), s.stream));
         }
         tm.lap("  indptr up + prepare");
-        { int rc = upload(h, s, raw_d[i], raw + s.nnz_begin, sizeof(uint16_t) * s.nnz); if (rc) return rc; }
-        { int rc = upload(h, s, colin_d[i], indices + s.nnz_begin, sizeof(int) * s.nnz); if (rc) return rc; }
         { int rc = upload(h, s, lut_d[i], q_lut, sizeof(double) * lut_len); if (rc) return rc; }
-        if (tm.on) { cudaStreamSynchronize(s.stream); tm.lap("  entries H2D (sync for timing)"); }
-        // tiles for the flat-tile passes, built on the device while the entry arrays are still arriving
+        // tiles for the flat-tile passes: they only need the read pointers, so they are built on the second stream before
+        // the entry arrays start to arrive
         {
-            int rc = build_tiles(h, s, s.indptr, s.n_rows, &s.tiles, &s.n_tiles, &s.n_long);
+            int rc = build_tiles(h, s, s.indptr, s.n_rows, &s.tiles, &s.n_tiles, &s.n_long, nullptr, s.aux);
             if (rc) return rc;
         }
         tm.lap("  tiles");
-        k_col_signature<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(
-            s.indptr, s.n_rows, colin_d[i], raw_d[i], K, ((unsigned long long)s.world_rank << 40), cnt_d[i], s.bad);
-        LAUNCH(h);
-        CU(cudaGetLastError());
+        // The entry arrays go up in chunks of whole reads; as soon as a chunk has landed, the second stream runs its share
+        // of the per-entry construction work -- the locus signatures, Q from the table, w*Y / totals / pisum0 -- while the
+        // copy engine moves the next chunk.  (With a locus renumbering Q has to wait for the global counts: old order.)
+        {
+            const long long per_chunk = 64LL << 20;                                     // entries
+            const int n_chunks = (int)std::max<long long>(1, std::min<long long>(32, (s.nnz + per_chunk - 1) / per_chunk));
+            long long r0 = 0;
+            for (int c = 0; c < n_chunks; ++c) {
+                long long r1 = s.n_rows;
+                if (c + 1 < n_chunks) {
+                    const long long target = s.nnz_begin + s.nnz / n_chunks * (c + 1);
+                    long long lo = r0, hi = s.n_rows;
+                    while (lo < hi) { const long long mid = (lo + hi) / 2; if (row_ptr(s.row_begin + mid) < target) lo = mid + 1; else hi = mid; }
+                    r1 = lo;
+                }
+                const long long e0 = row_ptr(s.row_begin + r0) - s.nnz_begin, e1 = row_ptr(s.row_begin + r1) - s.nnz_begin;
+                if (e1 > e0) {
+                    int rc = upload(h, s, raw_d[i] + e0, raw + s.nnz_begin + e0, sizeof(uint16_t) * (size_t)(e1 - e0));
+                    if (!rc) rc = upload(h, s, colin_d[i] + e0, indices + s.nnz_begin + e0, sizeof(int) * (size_t)(e1 - e0));
+                    if (rc) return rc;
+                }
+                CU(cudaEventRecord(s.ev_up, s.stream));
+                CU(cudaStreamWaitEvent(s.aux, s.ev_up, 0));
+                if (r1 > r0) {
+                    k_col_signature<<<grid_for(r1 - r0, 256, s.n_sm * 16), 256, 0, s.aux>>>(
+                        s.indptr + r0, r1 - r0, colin_d[i], raw_d[i], K, ((unsigned long long)s.world_rank << 40) + (unsigned long long)r0,
+                        cnt_d[i], s.bad);
+                    LAUNCH(h);
+                    if (!permute) {
+                        k_build_q<<<grid_for(e1 - e0, 256, s.n_sm * 16), 256, 0, s.aux>>>(raw_d[i] + e0, colin_d[i] + e0, lut_d[i], lut_len,
+                                                                                       nullptr, s.q + e0, s.col + e0, e1 - e0, s.bad);
+                        LAUNCH(h);
+                        k_row_init<<<grid_for(r1 - r0, 256, s.n_sm * 16), 256, 0, s.aux>>>(Csr{s.indptr + r0, s.col, s.q, r1 - r0}, K, s.wy + r0,
+                                                                                        s.scalars, s.pisum0);
+                        LAUNCH(h);
+                    }
+                    CU(cudaGetLastError());
+                }
+                r0 = r1;
+            }
+            // the main stream goes on once the second one is through
+            CU(cudaEventRecord(s.ev_up, s.aux));
+            CU(cudaStreamWaitEvent(s.stream, s.ev_up, 0));
+        }
+        if (tm.on) { cudaStreamSynchronize(s.stream); }
+        tm.lap("  entries H2D + signatures + Q");
     }
     if (tm.on) sync_all(h);
     tm.lap("column signatures");
@@ -1232,7 +1433,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
             CU(cudaSetDevice(s.dev));
             CU(cudaMemcpyAsync(&bad, s.bad, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
             CU(cudaStreamSynchronize(s.stream));
-            if (bad) return fail(TSC_ERR_ARG, "column index out of range [0, n_cols)");
+            if (bad & 1) return fail(TSC_ERR_ARG, "column index out of range [0, n_cols)");
         }
         std::vector<unsigned long long> cnt((size_t)K * 5);
         Shard& s0 = h->shards[0];
@@ -1275,7 +1476,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         if (h->n_dup_loci > 0) {
             for (auto& s : h->shards) {
                 CU(cudaSetDevice(s.dev));
-                CU(cudaMalloc(&s.rep, sizeof(int) * K));
+                CU(dev_malloc(&s.rep, sizeof(int) * K));
                 CU(cudaMemcpyAsync(s.rep, rep_internal.data(), sizeof(int) * K, cudaMemcpyHostToDevice, s.stream));
                 CU(cudaStreamSynchronize(s.stream));
             }
@@ -1287,20 +1488,25 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         CU(cudaSetDevice(s.dev));
         // (the K-sized arrays live in the shard's small slab, zeroed when it was allocated)
         CU(cudaMemcpyAsync(s.perm, h->perm.data(), sizeof(int) * K, cudaMemcpyHostToDevice, s.stream));
-        k_build_q<<<grid_for(s.nnz, 256, s.n_sm * 16), 256, 0, s.stream>>>(raw_d[i], colin_d[i], lut_d[i], lut_len,
-                                                                        permute ? s.perm : nullptr, s.q, s.col, s.nnz, s.bad);
-        LAUNCH(h);
-        CU(cudaGetLastError());
-        CU(cudaMemsetAsync(s.scalars, 0, sizeof(double) * 8, s.stream));
-        CU(cudaMallocHost(&s.st_host, sizeof(EmState) * 2));
+        if (permute) {
+            k_build_q<<<grid_for(s.nnz, 256, s.n_sm * 16), 256, 0, s.stream>>>(raw_d[i], colin_d[i], lut_d[i], lut_len, s.perm, s.q, s.col,
+                                                                            s.nnz, s.bad);
+            LAUNCH(h);
+            CU(cudaGetLastError());
+        }
+        static_assert(sizeof(EmState) * 2 <= 256, "two loop states fit a pinned slot");
+        if (!s.st_host) s.st_host = (EmState*)pinned_word_take();
+        if (!s.st_host) return fail(TSC_ERR_ALLOC, "no page-locked host memory for the loop state");
         CU(cudaEventCreateWithFlags(&s.ev_poll[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_poll[1], cudaEventDisableTiming));
         s.grid_rows = s.n_sm * 4;                   // 512-thread blocks, persistent grid-stride
         s.grid_tiles = s.n_sm * 2;                  // refined below from the occupancy of the tile kernel
         k_log_table<<<1, kLogTab, 0, s.stream>>>(s.log_tab);
         LAUNCH(h);
-        k_row_init<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(csr_of(s), s.wy, s.scalars, s.pisum0);
-        LAUNCH(h);
+        if (permute) {
+            k_row_init<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(csr_of(s), K, s.wy, s.scalars, s.pisum0);
+            LAUNCH(h);
+        }
         CU(cudaGetLastError());
         k_fill<<<grid_for(K, 256, 1 << 20), 256, 0, s.stream>>>(s.ones, K, 1.0);
         LAUNCH(h);
@@ -1346,7 +1552,7 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         CU(cudaMemcpyAsync(&bad, s.bad, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(part, s.scalars, sizeof(double) * 3, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaStreamSynchronize(s.stream));
-        if (bad) return fail(TSC_ERR_ARG, "raw score >= lut_len");
+        if (bad & 2) return fail(TSC_ERR_ARG, "raw score >= lut_len");
         Consts c;
         c.total_wt = part[0];
         c.ambig_wt = part[1];
@@ -1440,15 +1646,15 @@ extern "C" int tsc_get_row_info(tsc_handle* h, uint8_t* y_rows, double* w_rows) 
     for (auto& s : h->shards) {
         CU(cudaSetDevice(s.dev));
         uint8_t* yd = nullptr; double* wd = nullptr;
-        if (y_rows) CU(cudaMalloc(&yd, std::max<long long>(s.n_rows, 1)));
-        if (w_rows) CU(cudaMalloc(&wd, sizeof(double) * std::max<long long>(s.n_rows, 1)));
+        if (y_rows) CU(dev_malloc(&yd, std::max<long long>(s.n_rows, 1)));
+        if (w_rows) CU(dev_malloc(&wd, sizeof(double) * std::max<long long>(s.n_rows, 1)));
         k_row_info<<<grid_for(s.n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(csr_of(s), s.wy, yd, wd);
         LAUNCH(h);
         if (y_rows) CU(cudaMemcpyAsync(yh + s.row_begin, yd, s.n_rows, cudaMemcpyDeviceToHost, s.stream));
         if (w_rows) CU(cudaMemcpyAsync(wh + s.row_begin, wd, sizeof(double) * s.n_rows, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaStreamSynchronize(s.stream));
-        if (yd) cudaFree(yd);
-        if (wd) cudaFree(wd);
+        if (yd) dev_free(yd);
+        if (wd) dev_free(wd);
         h->d2h += (y_rows ? s.n_rows : 0) + (w_rows ? 8 * s.n_rows : 0);
     }
     if (compact) {
@@ -1558,7 +1764,7 @@ extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float
     Shard& s = h->shards[0];
     CU(cudaSetDevice(s.dev));
     double* zd = nullptr;
-    if (pass_id == 1) CU(cudaMalloc(&zd, sizeof(double) * std::max<long long>(s.nnz, 1)));
+    if (pass_id == 1) CU(dev_malloc(&zd, sizeof(double) * std::max<long long>(s.nnz, 1)));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
@@ -1604,11 +1810,22 @@ extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float
     cudaStreamSynchronize(s.stream);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    if (zd) cudaFree(zd);
+    if (zd) dev_free(zd);
     if (err != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("tsc_time_pass: ") + cudaGetErrorString(err));
     *mean_ms = ms / reps;
     return TSC_OK;
 }
+
+#ifdef TSC_ELL_TRACE
+// debug build only: start / end (globaltimer ns) of every CTA of the last k_ell<ELL_FUSED> launch on shard 0
+extern "C" int tsc_debug_ell_trace(tsc_handle* h, uint64_t* out, int32_t n_ctas) {
+    if (!h || !out) return fail(TSC_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(h->shards[0].dev));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out, g_ell_trace, sizeof(uint64_t) * 2 * std::min(n_ctas, 8192)));
+    return TSC_OK;
+}
+#endif
 
 extern "C" int tsc_get_kernel_times(tsc_handle* h, float* ms_out, int32_t max_n, int32_t* n_out) {
     if (!h) return fail(TSC_ERR_ARG, "handle is NULL");
@@ -1637,9 +1854,18 @@ static int launch_fused(tsc_handle* h, Shard& s, bool gated) {
     } else if (h->kernel == TSC_KERNEL_ELL) {
         // the clustered stream, then whatever does not fit a slice through the flat tiles of the residual CSR
         if (s.ell_slices > 0) {
-            EllArgs e{s.ell_stream, s.ell_index, s.ell_range, s.ell_slices, s.pt, s.acc, h->K, h->R_used, st, nullptr, nullptr, nullptr, 0, 0.0, nullptr, nullptr};
+            const bool measure = gated && s.ell_rebal_left > 0;
+            EllArgs e{s.ell_stream, s.ell_index, s.ell_range, s.ell_slices, s.pt, s.acc, h->K, h->R_used, st, nullptr, nullptr, nullptr, 0, 0.0, nullptr, nullptr,
+                      measure ? s.ell_cta_ns : nullptr};
             k_ell<ELL_FUSED><<<s.ell_grid, 32, kEllSmem, s.stream>>>(e);
             LAUNCH(h);
+            if (measure) {
+                // (the long-read records follow the slices in the stream: the slices end where they begin)
+                const unsigned end16 = (unsigned)((s.ell_long > 0 ? s.ell_slice_bytes : s.ell_bytes) >> 4);
+                k_ell_rebalance<<<1, 1024, 0, s.stream>>>(s.ell_index, s.ell_slices, end16, s.ell_grid, s.ell_range, s.ell_cta_ns, s.ell_rebal, st);
+                LAUNCH(h);
+                --s.ell_rebal_left;
+            }
         }
         if (s.ell_long > 0) {
             EllArgs e{s.ell_stream, s.ell_index + s.ell_slices, s.ell_lrange, s.ell_long, s.pt, s.acc, h->K, h->R_used, st, nullptr, nullptr, nullptr, 0, 0.0, nullptr, nullptr};
@@ -1742,10 +1968,10 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
     for (auto& s : h->shards) {
         CU(cudaSetDevice(s.dev));
         if (s.diffs_cap < T) {
-            if (s.diffs) cudaFree(s.diffs);
-            if (s.lnls) cudaFree(s.lnls);
-            CU(cudaMalloc(&s.diffs, sizeof(double) * T));
-            CU(cudaMalloc(&s.lnls, sizeof(double) * T));
+            if (s.diffs) dev_free(s.diffs);
+            if (s.lnls) dev_free(s.lnls);
+            CU(dev_malloc(&s.diffs, sizeof(double) * T));
+            CU(dev_malloc(&s.lnls, sizeof(double) * T));
             s.diffs_cap = T;
         }
         EmState st0{};
@@ -1877,7 +2103,7 @@ extern "C" int tsc_em(tsc_handle* h, int32_t max_iter, double eps, int32_t use_l
 // ------------------------------------------------------------------------------------------------- estep / mstep / lnl
 static int alloc_entries(Shard& s, double** p) {
     CU(cudaSetDevice(s.dev));
-    CU(cudaMalloc(p, sizeof(double) * std::max<long long>(s.nnz, 1)));
+    CU(dev_malloc(p, sizeof(double) * std::max<long long>(s.nnz, 1)));
     return TSC_OK;
 }
 
@@ -1903,7 +2129,7 @@ static int z_to_host(tsc_handle* h, int which, double* z_data) {
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(z_data + s.nnz_begin, zd, sizeof(double) * s.nnz, cudaMemcpyDeviceToHost, s.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-        cudaFree(zd);
+        dev_free(zd);
         if (e != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("posterior export: ") + cudaGetErrorString(e));
         h->d2h += sizeof(double) * s.nnz;
     }
@@ -1965,7 +2191,7 @@ extern "C" int tsc_mstep(tsc_handle* h, const double* z_data, double* pi_hat, do
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-        cudaFree(zd);
+        dev_free(zd);
         if (e != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("mstep: ") + cudaGetErrorString(e));
     }
     ALLREDUCE(h, s.tmp_c, (size_t)K, ncclFloat64, ncclSum);
@@ -1985,7 +2211,7 @@ extern "C" int tsc_calculate_lnl(tsc_handle* h, const double* z_data, const doub
     int rc = upload_pi_theta(h, pi, theta);
     if (rc) return rc;
     std::vector<double*> zd(h->shards.size(), nullptr);
-    auto free_all = [&]() { for (size_t i = 0; i < zd.size(); ++i) if (zd[i]) { cudaSetDevice(h->shards[i].dev); cudaFree(zd[i]); } };
+    auto free_all = [&]() { for (size_t i = 0; i < zd.size(); ++i) if (zd[i]) { cudaSetDevice(h->shards[i].dev); dev_free(zd[i]); } };
     for (size_t i = 0; i < h->shards.size(); ++i) {
         Shard& s = h->shards[i];
         if ((rc = alloc_entries(s, &zd[i]))) { free_all(); return rc; }
@@ -2032,12 +2258,12 @@ static int reassign_impl(tsc_handle* h, int method, double thresh, int initial, 
         cudaError_t e = cudaSuccess;
         const size_t rb = sizeof(int) * std::max<long long>(s.n_rows, 1);
         if (picks_h && method == TSC_CHOOSE) {
-            e = cudaMalloc(&picks_d, rb);
+            e = dev_malloc(&picks_d, rb);
             if (e == cudaSuccess) e = cudaMemcpyAsync(picks_d, picks_h + s.row_begin, sizeof(int) * s.n_rows, cudaMemcpyHostToDevice, s.stream);
             h->h2d += sizeof(int) * s.n_rows;
         }
-        if (e == cudaSuccess && nbest_h) e = cudaMalloc(&nbest_d, rb);
-        if (e == cudaSuccess && data) e = cudaMalloc(&data_d, sizeof(double) * std::max<long long>(s.nnz, 1));
+        if (e == cudaSuccess && nbest_h) e = dev_malloc(&nbest_d, rb);
+        if (e == cudaSuccess && data) e = dev_malloc(&data_d, sizeof(double) * std::max<long long>(s.nnz, 1));
         if (e == cudaSuccess && colsum) e = cudaMemsetAsync(s.colsum, 0, sizeof(double) * K, s.stream);
         if (e == cudaSuccess) {
             const double* ta = initial ? s.ones : s.pt_prev;
@@ -2056,9 +2282,9 @@ static int reassign_impl(tsc_handle* h, int method, double thresh, int initial, 
         if (e == cudaSuccess && nbest_h) { e = cudaMemcpyAsync(nbest_h + s.row_begin, nbest_d, sizeof(int) * s.n_rows, cudaMemcpyDeviceToHost, s.stream); h->d2h += sizeof(int) * s.n_rows; }
         if (e == cudaSuccess && data) { e = cudaMemcpyAsync(data + s.nnz_begin, data_d, sizeof(double) * s.nnz, cudaMemcpyDeviceToHost, s.stream); h->d2h += sizeof(double) * s.nnz; }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-        if (picks_d) cudaFree(picks_d);
-        if (nbest_d) cudaFree(nbest_d);
-        if (data_d) cudaFree(data_d);
+        if (picks_d) dev_free(picks_d);
+        if (nbest_d) dev_free(nbest_d);
+        if (data_d) dev_free(data_d);
         if (e != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("reassign: ") + cudaGetErrorString(e));
     }
     if (compact && nbest_rows) {
@@ -2095,16 +2321,16 @@ extern "C" int tsc_report(tsc_handle* h, double thresh, int32_t final_method, in
     int32_t* nbi_h = compact ? (nbest_init ? nbi_c.data() : nullptr) : nbest_init;
     int32_t* nbf_h = compact ? (nbest_final ? nbf_c.data() : nullptr) : nbest_final;
     std::vector<double*> out_d(h->shards.size(), nullptr);
-    auto free_all = [&]() { for (size_t i = 0; i < out_d.size(); ++i) if (out_d[i]) { cudaSetDevice(h->shards[i].dev); cudaFree(out_d[i]); } };
+    auto free_all = [&]() { for (size_t i = 0; i < out_d.size(); ++i) if (out_d[i]) { cudaSetDevice(h->shards[i].dev); dev_free(out_d[i]); } };
     for (size_t i = 0; i < h->shards.size(); ++i) {
         Shard& s = h->shards[i];
         CU(cudaSetDevice(s.dev));
         int *nbi_d = nullptr, *nbf_d = nullptr;
         const size_t rb = sizeof(int) * std::max<long long>(s.n_rows, 1);
-        cudaError_t e = cudaMalloc(&out_d[i], sizeof(double) * 6 * K);
+        cudaError_t e = dev_malloc(&out_d[i], sizeof(double) * 6 * K);
         if (e == cudaSuccess) e = cudaMemsetAsync(out_d[i], 0, sizeof(double) * 6 * K, s.stream);
-        if (e == cudaSuccess && nbi_h) e = cudaMalloc(&nbi_d, rb);
-        if (e == cudaSuccess && nbf_h) e = cudaMalloc(&nbf_d, rb);
+        if (e == cudaSuccess && nbi_h) e = dev_malloc(&nbi_d, rb);
+        if (e == cudaSuccess && nbf_h) e = dev_malloc(&nbf_d, rb);
         if (e == cudaSuccess) {
             ReportArgs g{thresh, final_method, nbi_d, nbf_d, out_d[i], K};
             launch_rows(h->G, [&](auto gg) {
@@ -2116,8 +2342,8 @@ extern "C" int tsc_report(tsc_handle* h, double thresh, int32_t final_method, in
         if (e == cudaSuccess && nbi_h) { e = cudaMemcpyAsync(nbi_h + s.row_begin, nbi_d, sizeof(int) * s.n_rows, cudaMemcpyDeviceToHost, s.stream); h->d2h += sizeof(int) * s.n_rows; }
         if (e == cudaSuccess && nbf_h) { e = cudaMemcpyAsync(nbf_h + s.row_begin, nbf_d, sizeof(int) * s.n_rows, cudaMemcpyDeviceToHost, s.stream); h->d2h += sizeof(int) * s.n_rows; }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-        if (nbi_d) cudaFree(nbi_d);
-        if (nbf_d) cudaFree(nbf_d);
+        if (nbi_d) dev_free(nbi_d);
+        if (nbf_d) dev_free(nbf_d);
         if (e != cudaSuccess) { free_all(); return fail(TSC_ERR_CUDA, std::string("report: ") + cudaGetErrorString(e)); }
     }
     for (size_t i = 0; i < h->shards.size(); ++i) h->shards[i].xchg_ptr = out_d[i];
@@ -2155,8 +2381,8 @@ extern "C" int tsc_choose_ties_colsum(tsc_handle* h, int32_t initial, const int3
         CU(cudaSetDevice(s.dev));
         int *nb_d = nullptr, *pk_d = nullptr;
         const size_t rb = sizeof(int) * std::max<long long>(s.n_rows, 1);
-        cudaError_t e = cudaMalloc(&nb_d, rb);
-        if (e == cudaSuccess) e = cudaMalloc(&pk_d, rb);
+        cudaError_t e = dev_malloc(&nb_d, rb);
+        if (e == cudaSuccess) e = dev_malloc(&pk_d, rb);
         if (e == cudaSuccess) e = cudaMemcpyAsync(nb_d, nb_h + s.row_begin, sizeof(int) * s.n_rows, cudaMemcpyHostToDevice, s.stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(pk_d, pk_h + s.row_begin, sizeof(int) * s.n_rows, cudaMemcpyHostToDevice, s.stream);
         h->h2d += 2 * sizeof(int) * s.n_rows;
@@ -2171,8 +2397,8 @@ extern "C" int tsc_choose_ties_colsum(tsc_handle* h, int32_t initial, const int3
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-        if (nb_d) cudaFree(nb_d);
-        if (pk_d) cudaFree(pk_d);
+        if (nb_d) dev_free(nb_d);
+        if (pk_d) dev_free(pk_d);
         if (e != cudaSuccess) return fail(TSC_ERR_CUDA, std::string("choose ties: ") + cudaGetErrorString(e));
     }
     ALLREDUCE(h, s.colsum, (size_t)K, ncclFloat64, ncclSum);

@@ -393,6 +393,7 @@ struct EllArgs {
     double thresh;
     const int* rowid;             // slices: 16 per record, the shard's read of each slot (-1 = empty); long reads: 1 per record
     int* nbest;                   // per read (optional): number of best hits
+    unsigned* cta_ns;             // FUSED (optional): how long each CTA took, in ns -- input of k_ell_rebalance
 };
 
 struct EllReassign {              // REASSIGN: per-slice view handed to the body
@@ -483,6 +484,7 @@ __device__ __forceinline__ void ell_body(const unsigned char* __restrict__ rec, 
         for (int t = 0; t < TM; ++t) n[t] = *reinterpret_cast<const double*>(accb + ao[t]) + n[t] * g;
 #pragma unroll
         for (int t = 0; t < TM; ++t) *reinterpret_cast<double*>(accb + ao[t]) = n[t];
+        __syncwarp();     // the other lane of this read slot loads these words in the next slice
     } else if (MODE == ELL_REASSIGN) {
         // z of the read, its maximum, how many entries reach it, and (conf) the mass at or above the threshold: private
         // over the lane's entries, then one exchange with the other lane of the read
@@ -511,6 +513,7 @@ __device__ __forceinline__ void ell_body(const unsigned char* __restrict__ rec, 
                 }
 #pragma unroll
                 for (int t = 0; t < TM; ++t) *reinterpret_cast<double*>(accb + ao[t] * (kEllReads * 8)) = n[t];
+                __syncwarp();
             } else if (re.method == 2) {                 // average: 1/nbest on every best hit (a few per read)
                 const double v = nb > 0 ? 1.0 / (double)nb : 0.0;
 #pragma unroll
@@ -726,10 +729,27 @@ __device__ __noinline__ void ell_long_big(const unsigned char* __restrict__ rec,
     }
 }
 
+__device__ __forceinline__ unsigned long long ell_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+#ifdef TSC_ELL_TRACE
+// debug build only (tools/profile/trace_ell.py): per-CTA start / end times of the last k_ell<ELL_FUSED> launch
+__device__ unsigned long long g_ell_trace[2 * 8192];
+__device__ __forceinline__ unsigned long long ell_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 template <int MODE>
 __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     if (a.st && a.st->done) return;
+#ifdef TSC_ELL_TRACE
+    if (MODE == ELL_FUSED && threadIdx.x == 0 && blockIdx.x < 8192) g_ell_trace[2 * blockIdx.x] = ell_now();
+#endif
+    unsigned long long t_start = 0;
+    if (MODE == ELL_FUSED && a.cta_ns) t_start = ell_globaltimer();
     // FUSED: s_acc [kEllWin + 2][kEllReads] (last two rows = dummies) | s_pt [kEllWin + 8] ([kEllWin..] = 0 for empty slots)
     // LNL:   s_pt [kEllWin + 8] | s_in [kEllWin + 8] | log table
     double* s_acc = reinterpret_cast<double*>(s_raw);
@@ -842,6 +862,58 @@ __global__ void __launch_bounds__(32) k_ell(const EllArgs a) {
         lnl_local = group_sum<32>(lnl_local, 0xffffffffu);
         if (lane == 0) a.partials[blockIdx.x] = lnl_local;
     }
+#ifdef TSC_ELL_TRACE
+    if (MODE == ELL_FUSED && threadIdx.x == 0 && blockIdx.x < 8192) g_ell_trace[2 * blockIdx.x + 1] = ell_now();
+#endif
+    if (MODE == ELL_FUSED && a.cta_ns && threadIdx.x == 0) a.cta_ns[blockIdx.x] = (unsigned)(ell_globaltimer() - t_start);
+}
+
+// Measured re-partition of the slice stream.  The byte-balanced runs of k_ell_ranges do not finish together: how fast a
+// warp gets through its run depends on the loci it covers (how often the window moves, how long the slices are), and the
+// slowest warp of the 1776 sets the kernel time -- a CTA trace on B200 shows the last run ending 11 % after the median
+// one, at every problem size (profiles/r2_cta_trace.md).  So the per-iteration kernel reports how long every CTA took and
+// this kernel, run after the first iterations of a model, moves the boundaries to where equal shares of the MEASURED time
+// fall: time is taken as uniform per byte inside an old run, new boundary k is the first record at or after the byte
+// where k/G of the total time has passed.  One block; range[] is rewritten in place for the next launch.
+__global__ void __launch_bounds__(1024) k_ell_rebalance(const int4* __restrict__ index, long long n_slices, unsigned end_off16,
+                                                        int G, long long* __restrict__ range, const unsigned* __restrict__ cta_ns,
+                                                        double* __restrict__ scratch /* 2 * (G + 1) */, const EmState* __restrict__ st) {
+    if (st && st->done) return;                      // the launch that would have measured was skipped too
+    double* S = scratch;                              // S[w] = time of the runs before w
+    double* B = scratch + G + 1;                      // B[w] = first byte / 16 of run w
+    for (int w = threadIdx.x; w <= G; w += blockDim.x) {
+        const long long r = range[w];
+        B[w] = (r >= n_slices) ? (double)end_off16 : (double)(unsigned)index[r].x;
+    }
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int w = 0; w < G; ++w) { S[w] = acc; acc += (double)max(cta_ns[w], 1u); }
+        S[G] = acc;
+    }
+    __syncthreads();
+    const double total = S[G];
+    long long mine[4];                                // G <= 4096 boundaries, computed before anything is overwritten
+    int nm = 0;
+    for (int k = threadIdx.x; k <= G && nm < 4; k += blockDim.x, ++nm) {
+        long long rec;
+        if (k == 0) rec = 0;
+        else if (k == G) rec = n_slices;
+        else {
+            const double tau = total * (double)k / (double)G;
+            int lo = 0, hi = G - 1;                   // last run w with S[w] <= tau
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (S[mid] <= tau) lo = mid; else hi = mid - 1; }
+            const double span = S[lo + 1] - S[lo];
+            const double frac = span > 0.0 ? (tau - S[lo]) / span : 0.0;
+            const double byte16 = B[lo] + frac * (B[lo + 1] - B[lo]);
+            long long a = 0, b = n_slices;            // first record that starts at or after that byte
+            while (a < b) { const long long mid = (a + b) >> 1; if ((double)(unsigned)index[mid].x < byte16) a = mid + 1; else b = mid; }
+            rec = a;
+        }
+        mine[nm] = rec;
+    }
+    __syncthreads();
+    nm = 0;
+    for (int k = threadIdx.x; k <= G && nm < 4; k += blockDim.x, ++nm) range[k] = mine[nm];
 }
 
 

@@ -153,7 +153,7 @@ __global__ void k_build_q(const uint16_t* __restrict__ raw, const int* __restric
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < nnz; i += stride) {
         const int s = raw[i];
-        if (s >= lut_len) { *bad = 1; q[i] = 0.0; } else q[i] = __ldg(lut + s);
+        if (s >= lut_len) { atomicOr(bad, 2); q[i] = 0.0; } else q[i] = __ldg(lut + s);
         col[i] = perm ? __ldg(perm + col_in[i]) : col_in[i];
     }
 }
@@ -179,7 +179,7 @@ __global__ void k_col_signature(const long long* __restrict__ indptr, long long 
         const unsigned long long rk = mix64(row_key0 + (unsigned long long)r);
         for (long long k = indptr[r]; k < indptr[r + 1]; ++k) {
             const int c = col[k];
-            if (c < 0 || c >= n_cols) { *bad = 1; continue; }
+            if (c < 0 || c >= n_cols) { atomicOr(bad, 1); continue; }
             const unsigned long long e = rk ^ ((unsigned long long)raw[k] * 0x9e3779b97f4a7c15ULL);
             atomicAdd(sig + c, 1ULL);
             atomicAdd(sig + n_cols + c, mix64(e));
@@ -192,7 +192,7 @@ __global__ void k_col_signature(const long long* __restrict__ indptr, long long 
 
 // w_i = max_j Q_ij (model.py:690); wy_i = w_i * Y_i with Y_i = [row has > 1 entries] (model.py:679);
 // partial[0] += sum w, partial[1] += sum wy, partial[2] = max w; pisum0_j += Q_ij over unique reads (model.py:699).
-__global__ void k_row_init(Csr a, double* __restrict__ wy, double* __restrict__ partial,
+__global__ void k_row_init(Csr a, int n_cols, double* __restrict__ wy, double* __restrict__ partial,
                            double* __restrict__ pisum0) {
     __shared__ double s_red[32];
     double sw = 0, swy = 0, mw = 0;
@@ -207,7 +207,10 @@ __global__ void k_row_init(Csr a, double* __restrict__ wy, double* __restrict__ 
         sw += w;
         if (amb) swy += w;
         mw = fmax(mw, w);
-        if (!amb && e > s) atomicAdd(pisum0 + a.col[s], a.q[s]);
+        if (!amb && e > s) {
+            const int c = a.col[s];          // (may run before the loci have been validated: stay in bounds)
+            if ((unsigned)c < (unsigned)n_cols) atomicAdd(pisum0 + c, a.q[s]);
+        }
     }
     sw = block_sum(sw, s_red);
     if (threadIdx.x == 0) atomicAdd(partial + 0, sw);

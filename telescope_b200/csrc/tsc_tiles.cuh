@@ -129,6 +129,19 @@ constexpr int kScrN = 136;                     // per-warp scratch: the tile's n
 constexpr int kScrG = 132;                     //                   per-read totals, then per-read scale g
 constexpr int kScratch = kScrN + kScrG;        // doubles per warp
 
+#ifndef TSC_TILE_PREFETCH
+#define TSC_TILE_PREFETCH 1
+#endif
+constexpr bool TILE_PREFETCH = TSC_TILE_PREFETCH != 0;
+// [p, p + bytes) -> L2, as one TMA bulk prefetch (SASS UBLKPF.L2): 16-byte granules, so the range is widened to them;
+// the entry arrays carry 256 entries of padding behind the last tile
+__device__ __forceinline__ void tile_prefetch_l2(const void* p, unsigned bytes) {
+    const unsigned long long a = reinterpret_cast<unsigned long long>(p);
+    const unsigned long long a0 = a & ~15ULL;
+    const unsigned n = (unsigned)((a + bytes + 15ULL - a0) & ~15ULL);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
+}
+
 template <bool SMEM_TAB>
 __device__ __forceinline__ double gather_pt(const double* __restrict__ pt, const double* s_tab, int s_cols, int c) {
     if (SMEM_TAB) return (c < s_cols) ? s_tab[c] : __ldg(pt + c);
@@ -214,8 +227,8 @@ k_tiles(const TileArgs a) {
         const int row0 = d0.z;
         const int end = d0.w & 0xff, nrows = (d0.w >> 16) & 0xff;
         const unsigned F[4] = {fl.x, fl.y, fl.z, fl.w};
-        // next tile's descriptor: pulled towards the SM while this tile is processed (costs no registers)
-        const long long tn = (t + nwarps < n_tiles) ? t + nwarps : t;
+        // the descriptor of the tile after next: pulled into L2 while this tile is processed (costs no registers)
+        const long long tn = (t + 2 * nwarps < n_tiles) ? t + 2 * nwarps : t;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(tiles + tn));
 
         if (end == 0) {
@@ -280,6 +293,13 @@ k_tiles(const TileArgs a) {
         for (int e = 0; e < 4; ++e) {      // 8 loads in flight before anything is consumed (entries past the tile
             cc[e] = ld_stream(colp + 32 * e);                    // are padding or the next tile's: harmless)
             qq[e] = ld_stream(qp + 32 * e);
+        }
+        // ... and the NEXT tile's entries go to L2 now (one lane asks the TMA unit: two bulk prefetches), so that the
+        // loads above are L2 hits one iteration from now; its descriptor was prefetched an iteration ago
+        if (TILE_PREFETCH && lane == 0 && t + nwarps < n_tiles) {
+            const long long nb = __ldg(reinterpret_cast<const long long*>(tiles + t + nwarps));
+            tile_prefetch_l2(q + nb, 128 * sizeof(double));
+            tile_prefetch_l2(col + nb, 128 * sizeof(int));
         }
         // w*Y of my read (row phase below), requested early
         double w_mine = 1.0;

@@ -439,6 +439,15 @@ static int tiles_grid(const Shard& s, long long n_tiles) {
     return (int)std::max<long long>(1, std::min<long long>(s.grid_tiles, (n_tiles + kTileWarps - 1) / kTileWarps));
 }
 
+static int build_tiles(tsc_handle* h, Shard& s, const long long* indptr_d, long long n_rows, Tile** tiles_out,
+                       long long* n_tiles_out, long long* n_long_out, struct Arena* arena, cudaStream_t st);
+// the shard-wide tile list, built on first use (see create_attempt)
+static int ensure_tiles(tsc_handle* h, Shard& s) {
+    if (s.tiles || s.n_rows == 0) return TSC_OK;
+    CU(cudaSetDevice(s.dev));
+    return build_tiles(h, s, s.indptr, s.n_rows, &s.tiles, &s.n_tiles, &s.n_long, nullptr, nullptr);
+}
+
 template <int MODE>
 static void launch_tiles(const Shard& s, const TileArgs& a, bool smem_tab, int long8_override = -1) {
     const size_t scratch = sizeof(double) * kTileWarps * kScratch;
@@ -748,7 +757,7 @@ static int upload(tsc_handle* h, Shard& s, void* dst, const void* src, size_t by
     if (bytes == 0) return TSC_OK;
     h->h2d += (long long)bytes;
     int threads = (int)std::thread::hardware_concurrency() / std::max(1, h->n_procs * (int)h->shards.size());
-    threads = std::max(1, std::min(threads - 2, 12));          // (two cores stay free for this thread and the driver's)
+    threads = std::max(1, std::min(threads, 8));               // (12 threads measured slower than 8 on the 16-core host)
     if (bytes < (32u << 20) || host_is_pinned(src) || getenv("TELESCOPE_B200_NO_STAGING")) {
         CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.stream));
         return TSC_OK;
@@ -899,7 +908,7 @@ struct SlabPlan {            // sizes first, one cudaMalloc, then the pointers
 };
 
 static int build_tiles(tsc_handle* h, Shard& s, const long long* indptr_d, long long n_rows, Tile** tiles_out,
-                       long long* n_tiles_out, long long* n_long_out, Arena* arena = nullptr, cudaStream_t st = nullptr) {
+                       long long* n_tiles_out, long long* n_long_out, Arena* arena, cudaStream_t st) {
     if (!st) st = s.stream;
     const int n_chunks = (int)((n_rows + kChunkRows - 1) / kChunkRows);
     DevBuf tmp;
@@ -1059,7 +1068,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
         CU(dev_malloc(&s.ell_stream, (size_t)total));
         lap("  ell stream malloc");
         if (n_slices > 0) {
-            k_ell_fill<<<grid_for(n_slices * 32, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, s.col, s.q, s.wy, sorted, n_short, n_slices,
+            k_ell_fill<<<grid_for(n_slices * 32, kFillWarps * 32, s.n_sm * 32), kFillWarps * 32, 0, s.stream>>>(s.indptr, s.col, s.q, s.wy, sorted, n_short, n_slices,
                                                                                        s.ell_index, rec_off, s.ell_stream);
             LAUNCH(h);
         }
@@ -1089,7 +1098,7 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
             if ((rc = split(rec_off, n_slices, warps, &s.ell_grid, &s.ell_range))) return rc;
             // the first iterations of the model measure how long every run takes and move the boundaries accordingly
             const char* rb_env = getenv("TELESCOPE_B200_REBALANCE");
-            s.ell_rebal_left = rb_env ? atoi(rb_env) : 2;
+            s.ell_rebal_left = rb_env ? atoi(rb_env) : 4;
             if (s.ell_grid < 2 || s.ell_grid + 1 > 4096) s.ell_rebal_left = 0;
             if (s.ell_rebal_left > 0) {
                 CU(dev_malloc(&s.ell_cta_ns, sizeof(unsigned) * s.ell_grid));
@@ -1149,15 +1158,15 @@ static int build_ell(tsc_handle* h, Shard& s, StageTimer& tm, Arena* arena) {
                 const unsigned long long start[2] = {0ULL, ((unsigned long long)s.res_amb_rows << kResShift) | (unsigned long long)s.res_amb_nnz};
                 CU(cudaMemcpyAsync(counters + 4, start, sizeof(start), cudaMemcpyHostToDevice, s.stream));
             }
-            k_res_append<<<grid_for(n_rows * 8, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, key, n_stream_keys, counters + 4,
+            k_res_append<<<grid_for(n_rows, 256, s.n_sm * 16), 256, 0, s.stream>>>(s.indptr, n_rows, s.col, s.q, s.wy, key, n_stream_keys, counters + 4,
                                                                                      s.res_indptr, s.res_col, s.res_q, s.res_wy, s.res_rowid);
             LAUNCH(h);
             CU(cudaMemcpyAsync(s.res_indptr + s.res_rows, &s.res_nnz, sizeof(long long), cudaMemcpyHostToDevice, s.stream));
             CU(cudaGetLastError());
             CU(cudaStreamSynchronize(s.stream));
-            int rc = build_tiles(h, s, s.res_indptr, s.res_rows, &s.res_tiles, &s.res_n_tiles, &s.res_n_long, arena);
+            int rc = build_tiles(h, s, s.res_indptr, s.res_rows, &s.res_tiles, &s.res_n_tiles, &s.res_n_long, arena, nullptr);
             if (!rc && s.res_amb_rows > 0)
-                rc = build_tiles(h, s, s.res_indptr, s.res_amb_rows, &s.res_tiles_amb, &s.res_amb_tiles, &s.res_amb_long, arena);
+                rc = build_tiles(h, s, s.res_indptr, s.res_amb_rows, &s.res_tiles_amb, &s.res_amb_tiles, &s.res_amb_long, arena, nullptr);
             if (rc) return rc;
             lap("  residual copy+tiles");
         }
@@ -1368,9 +1377,9 @@ static int create_attempt(tsc_handle* h, const tsc_config& cfg, const CreateInpu
         }
         tm.lap("  indptr up + prepare");
         { int rc = upload(h, s, lut_d[i], q_lut, sizeof(double) * lut_len); if (rc) return rc; }
-        // tiles for the flat-tile passes: they only need the read pointers, so they are built on the second stream before
-        // the entry arrays start to arrive
-        {
+        // tiles over the whole shard: only the flat-tile kernel family iterates with them; with the clustered stream they
+        // serve nothing but the posterior export (estep / self.z) and are built when that is first asked for
+        if (h->kernel == TSC_KERNEL_TILES) {
             int rc = build_tiles(h, s, s.indptr, s.n_rows, &s.tiles, &s.n_tiles, &s.n_long, nullptr, s.aux);
             if (rc) return rc;
         }
@@ -1764,6 +1773,7 @@ extern "C" int tsc_time_pass(tsc_handle* h, int32_t pass_id, int32_t reps, float
     Shard& s = h->shards[0];
     CU(cudaSetDevice(s.dev));
     double* zd = nullptr;
+    if (pass_id == 1) { int rc = ensure_tiles(h, s); if (rc) return rc; }
     if (pass_id == 1) CU(dev_malloc(&zd, sizeof(double) * std::max<long long>(s.nnz, 1)));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
@@ -2116,6 +2126,7 @@ static int z_to_host(tsc_handle* h, int which, double* z_data) {
         const double* ta = which == 0 ? s.tmp_c : which == 1 ? s.pt_prev : s.ones;
         const double* tu = which == 0 ? s.tmp_a : which == 1 ? s.pi_prev : s.ones;
         if (h->kernel != TSC_KERNEL_ROWS) {
+            if ((rc = ensure_tiles(h, s))) { dev_free(zd); return rc; }
             TileArgs a{};
             a.tiles = s.tiles; a.n_tiles = s.n_tiles; a.q = s.q; a.col = s.col; a.tab_amb = ta; a.tab_uni = tu;
             a.K = h->K; a.z_out = zd;

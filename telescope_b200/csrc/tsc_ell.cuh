@@ -266,20 +266,31 @@ __global__ void k_ell_ranges(const long long* __restrict__ rec_off, long long n_
     range[w] = lo;
 }
 
-// One warp per slice writes its record and completes its index entry.
-__global__ void __launch_bounds__(256) k_ell_fill(const long long* __restrict__ ip, const int* __restrict__ col,
-                                                  const double* __restrict__ q, const double* __restrict__ wy,
-                                                  const int* __restrict__ sorted, long long n_cand, long long n_slices,
-                                                  int4* __restrict__ hdr, const long long* __restrict__ rec_off,
-                                                  unsigned char* __restrict__ stream) {
-    const int lane = threadIdx.x & 31, r = lane & 15, h = lane >> 4;
+// One warp per slice writes its record and completes its index entry.  The 16 reads of a slice lie anywhere in the
+// shard's CSR, so they are first copied read by read, lane-consecutive (coalesced), into shared memory and transposed
+// into the record's (step, lane) layout from there: lane (r, h) taking q[b_r + 2t + h] straight from global memory read
+// every 32-byte sector in two different steps and fetched 31 B of DRAM per entry instead of 12 (ncu, profiles/).
+constexpr int kFillWarps = 4;
+constexpr int kFillQStride = 2 * kEllTMax + 1;        // doubles per read: odd, so the 16 reads of a step hit 16 bank pairs
+constexpr int kFillCStride = 2 * kEllTMax + 4;        // bytes per read: 13 words, injective modulo the 32 banks
+
+__global__ void __launch_bounds__(kFillWarps * 32) k_ell_fill(const long long* __restrict__ ip, const int* __restrict__ col,
+                                                              const double* __restrict__ q, const double* __restrict__ wy,
+                                                              const int* __restrict__ sorted, long long n_cand, long long n_slices,
+                                                              int4* __restrict__ hdr, const long long* __restrict__ rec_off,
+                                                              unsigned char* __restrict__ stream) {
+    __shared__ double s_q[kFillWarps][kEllReads * kFillQStride];
+    __shared__ unsigned char s_c[kFillWarps][kEllReads * kFillCStride];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, r = lane & 15, h = lane >> 4;
+    double* sq = s_q[wib];
+    unsigned char* sc = s_c[wib];
     long long s = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
     for (; s < n_slices; s += stride) {
         const int4 hd = hdr[s];
         const long long off = rec_off[s];
         unsigned char* rec = stream + off;
-        __syncwarp();
+        __syncwarp();                                  // (the previous slice's shared-memory reads are done)
         if (lane == 0) hdr[s].x = (int)(off >> 4);
         const long long p = s * kEllReads + r;
         const int read = (p < n_cand) ? sorted[p] : -1;
@@ -287,6 +298,19 @@ __global__ void __launch_bounds__(256) k_ell_fill(const long long* __restrict__ 
         int len = 0;
         if (read >= 0) { b = ip[read]; len = (int)(ip[read + 1] - b); }
         if (h == 0) reinterpret_cast<double*>(rec)[r] = (read >= 0) ? wy[read] : 0.0;
+        // ---- read by read into shared memory (a slice member has at most 2 * kEllTMax = 48 entries)
+#pragma unroll 4
+        for (int m = 0; m < kEllReads; ++m) {
+            const long long bm = __shfl_sync(0xffffffffu, b, m);
+            const int lm = __shfl_sync(0xffffffffu, len, m);
+            if (lane < lm) { sq[m * kFillQStride + lane] = q[bm + lane]; sc[m * kFillCStride + lane] = (unsigned char)(col[bm + lane] & (kEllWin - 1)); }
+            if (lane + 32 < lm) {
+                sq[m * kFillQStride + lane + 32] = q[bm + lane + 32];
+                sc[m * kFillCStride + lane + 32] = (unsigned char)(col[bm + lane + 32] & (kEllWin - 1));
+            }
+        }
+        __syncwarp();
+        // ---- ... and out in the record's layout: lane (r, h) owns entries 2t + h of read r
         const int T = hd.z & 0xff;
         unsigned char* dc = rec + kEllHdr;
         double* qq = reinterpret_cast<double*>(rec + kEllHdr + 32 * T);
@@ -294,7 +318,7 @@ __global__ void __launch_bounds__(256) k_ell_fill(const long long* __restrict__ 
             const int k = 2 * t + h;
             double qv = 0.0;
             int d = kEllWin + h;                                      // empty slot: this half-warp's dummy row
-            if (k < len) { qv = q[b + k]; d = col[b + k] & (kEllWin - 1); }
+            if (k < len) { qv = sq[r * kFillQStride + k]; d = sc[r * kFillCStride + k]; }
             dc[t * 32 + lane] = (unsigned char)d;
             qq[t * 32 + lane] = qv;
         }
@@ -335,9 +359,12 @@ __global__ void k_res_count(const long long* __restrict__ ip, long long n_rows, 
     }
 }
 
-// 8 lanes per read; a residual read takes its place (read slot, first entry) from one packed atomic, so the read
-// pointers come out increasing in slot order whatever order the reads arrive in.  Ambiguous reads fill the front of
-// the residual (the fused kernel only visits those), unique reads the rest: cursor[1] starts where the front ends.
+// One lane per read.  A residual read takes its place (read slot, first entry) from a packed atomic, so the read
+// pointers come out increasing in slot order whatever order the reads arrive in.  Ambiguous reads fill the front of the
+// residual (the fused kernel only visits those), unique reads the rest: cursor[1] starts where the front ends.  The
+// unique reads -- a fifth of all reads, one entry each -- take their places with ONE atomic per warp (ballot + rank:
+// ten million single atomics on the same word were most of this kernel's time) and copy their entry themselves; the
+// ambiguous residual reads (few) are then copied by the whole warp, one read at a time.
 __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict__ ip, long long n_rows, const int* __restrict__ col,
                                                     const double* __restrict__ q, const double* __restrict__ wy,
                                                     const int* __restrict__ key, int n_stream_keys,
@@ -345,22 +372,44 @@ __global__ void __launch_bounds__(256) k_res_append(const long long* __restrict_
                                                     long long* __restrict__ ip_out, int* __restrict__ col_out,
                                                     double* __restrict__ q_out, double* __restrict__ wy_out,
                                                     int* __restrict__ rowid_out) {
-    const int lane = threadIdx.x & 7;
-    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
-    long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
-    const long long stride = ((long long)gridDim.x * blockDim.x) >> 3;
-    const long long r_end = ((n_rows + stride - 1) / stride) * stride;       // every group runs the same trip count
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long r_end = ((n_rows + stride - 1) / stride) * stride;       // every warp runs the same trip count
     for (; r < r_end; r += stride) {
         long long b = 0, e = 0;
         bool res = false;
         if (r < n_rows) { b = ip[r]; e = ip[r + 1]; res = (key == nullptr || key[r] < 0 || key[r] >= n_stream_keys); }
-        unsigned long long old = 0;     // cursor[0]: ambiguous reads (the front of the residual), cursor[1]: unique reads
-        if (res && lane == 0) old = atomicAdd(cursor + ((e - b >= 2) ? 0 : 1), (1ULL << kResShift) | (unsigned long long)(e - b));
-        old = __shfl_sync(gmask, old, (threadIdx.x & 31) & ~7);
-        if (!res) continue;
-        const long long rp = (long long)(old >> kResShift), o = (long long)(old & ((1ULL << kResShift) - 1ULL));
-        if (lane == 0) { ip_out[rp] = o; wy_out[rp] = wy[r]; rowid_out[rp] = (int)r; }
-        for (long long k = b + lane; k < e; k += 8) { col_out[o + (k - b)] = col[k]; q_out[o + (k - b)] = q[k]; }
+        const bool uni = res && (e - b) == 1, amb = res && (e - b) >= 2;
+        // ---- unique reads: one packed atomic for the warp's reads, each lane places its own entry
+        const unsigned um = __ballot_sync(0xffffffffu, uni);
+        if (um) {
+            const unsigned long long n = (unsigned long long)__popc(um);
+            unsigned long long base = 0;
+            if (lane == (__ffs(um) - 1)) base = atomicAdd(cursor + 1, (n << kResShift) | n);
+            base = __shfl_sync(0xffffffffu, base, __ffs(um) - 1);
+            if (uni) {
+                const long long k = (long long)__popc(um & lt);
+                const long long rp = (long long)(base >> kResShift) + k, o = (long long)(base & ((1ULL << kResShift) - 1ULL)) + k;
+                ip_out[rp] = o; wy_out[rp] = wy[r]; rowid_out[rp] = (int)r;
+                col_out[o] = col[b]; q_out[o] = q[b];
+            }
+        }
+        // ---- ambiguous residual reads: the owner lane takes the place, the warp copies
+        unsigned am = __ballot_sync(0xffffffffu, amb);
+        unsigned long long old = 0;
+        if (amb) old = atomicAdd(cursor + 0, (1ULL << kResShift) | (unsigned long long)(e - b));
+        while (am) {
+            const int src = __ffs(am) - 1;
+            am &= am - 1;
+            const long long bb = __shfl_sync(0xffffffffu, b, src), ee = __shfl_sync(0xffffffffu, e, src);
+            const unsigned long long oo = __shfl_sync(0xffffffffu, old, src);
+            const long long rr = __shfl_sync(0xffffffffu, r, src);
+            const long long rp = (long long)(oo >> kResShift), o = (long long)(oo & ((1ULL << kResShift) - 1ULL));
+            if (lane == 0) { ip_out[rp] = o; wy_out[rp] = wy[rr]; rowid_out[rp] = (int)rr; }
+            for (long long k = bb + lane; k < ee; k += 32) { col_out[o + (k - bb)] = col[k]; q_out[o + (k - bb)] = q[k]; }
+        }
     }
 }
 
@@ -885,10 +934,29 @@ __global__ void __launch_bounds__(1024) k_ell_rebalance(const int4* __restrict__
         const long long r = range[w];
         B[w] = (r >= n_slices) ? (double)end_off16 : (double)(unsigned)index[r].x;
     }
-    if (threadIdx.x == 0) {
-        double acc = 0.0;
-        for (int w = 0; w < G; ++w) { S[w] = acc; acc += (double)max(cta_ns[w], 1u); }
-        S[G] = acc;
+    {   // exclusive prefix sums of the run times: four consecutive runs per thread, warp scan, scan of the warp totals
+        __shared__ double s_w[32];
+        const int w0 = threadIdx.x * 4;
+        double v[4], mine = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] = (w0 + i < G) ? (double)max(cta_ns[w0 + i], 1u) : 0.0; mine += v[i]; }
+        double x = mine;
+        const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const double y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) s_w[wp] = x;
+        __syncthreads();
+        if (wp == 0) {
+            double t = s_w[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const double y = __shfl_up_sync(0xffffffffu, t, d); if (lane >= d) t += y; }
+            s_w[lane] = t;
+        }
+        __syncthreads();
+        double run = x - mine + (wp ? s_w[wp - 1] : 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { if (w0 + i < G) S[w0 + i] = run; run += v[i]; }
+        if (threadIdx.x == 1023) S[G] = s_w[31];
     }
     __syncthreads();
     const double total = S[G];

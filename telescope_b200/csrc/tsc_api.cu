@@ -275,7 +275,7 @@ struct Shard {
     // peer-memory transport (tsc_peer.cuh): this GPU's exchange buffer, every rank's buffer as mapped here
     unsigned char* peer_own = nullptr;
     std::vector<unsigned char*> peer_map;       // world entries; [world_rank] == peer_own
-    std::vector<char> peer_opened;              // mapped with cudaIpcOpenMemHandle (closed at destruction)
+    std::vector<char> peer_opened;              // mapped with cudaIpcOpenMemHandle by this model (kept open in g_ipc)
     unsigned char** peer_ptrs_d = nullptr;
     double* tail_partials = nullptr;
     unsigned* tail_ticket = nullptr;
@@ -544,6 +544,8 @@ extern "C" void tsc_config_default(tsc_config* cfg) {
     cfg->transport = TSC_TRANSPORT_AUTO;
 }
 
+static void peer_buffer_release(void* buf);
+
 static void free_shard(Shard& s) {
     cudaSetDevice(s.dev);
     if (s.stream) cudaStreamSynchronize(s.stream);
@@ -555,9 +557,8 @@ static void free_shard(Shard& s) {
                     s.peer_ptrs_d, s.tail_partials, s.tail_ticket, s.peer_err, s.log_tab};
     for (void* p : ptrs) if (p && !s.in_slab(p)) dev_free(p);
     for (auto& b : s.slabs) dev_free(b.first);
-    for (size_t r = 0; r < s.peer_map.size(); ++r)
-        if (r < s.peer_opened.size() && s.peer_opened[r] && s.peer_map[r]) cudaIpcCloseMemHandle(s.peer_map[r]);
-    if (s.peer_own) dev_free(s.peer_own);      // (a block shared through IPC is not in the cache: plain cudaFree)
+    // (mappings of other processes' buffers stay open in g_ipc for the next model)
+    peer_buffer_release(s.peer_own);
     pinned_word_give(s.st_host);
     for (auto& e : s.ev_poll) if (e) cudaEventDestroy(e);
     for (auto& e : s.ev_k) if (e) cudaEventDestroy(e);
@@ -584,6 +585,19 @@ static void peer_geometry(int K, int* kpad, int* nb, int* cap) {
     *cap = *kpad + 64;          // larger reductions go through the inbox in pieces
 }
 
+// Exchange buffers that other processes map (one process per GPU) and the mappings of theirs are kept for the life of
+// the process: cudaIpcOpenMemHandle costs milliseconds per peer -- tens when eight processes do it at once -- and a
+// process that builds model after model (assign + resume, a service, the benchmark's repeated jobs) meets the same peers
+// with the same buffers every time.  A destroyed model hands its exported buffer back to `idle`; the next model of the same
+// geometry re-exports it under the same handle, and its peers find the handle among the mappings they kept open.
+struct IpcCache {
+    std::mutex mu;
+    struct Own { int dev; size_t bytes; unsigned char* buf; cudaIpcMemHandle_t hd; };
+    std::vector<Own> idle, live;
+    std::map<std::string, void*> opened;          // 64 handle bytes -> mapping in this process
+};
+static IpcCache g_ipc;
+
 static int peer_buffer_alloc(int dev, int K, int world, unsigned char** out, bool ipc) {
     int kpad, nb, cap;
     peer_geometry(K, &kpad, &nb, &cap);
@@ -598,19 +612,55 @@ static int peer_buffer_alloc(int dev, int K, int world, unsigned char** out, boo
 
 extern "C" int tsc_peer_buffer_create(int32_t device, int32_t n_cols, int32_t world, void** buf_out, void* ipc_handle64_out) {
     if (!buf_out || !ipc_handle64_out || n_cols <= 0 || world <= 0) return fail(TSC_ERR_ARG, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    int kpad, nb, cap;
+    peer_geometry(n_cols, &kpad, &nb, &cap);
+    const size_t bytes = 8 * peer_buffer_words(world, kpad, nb, cap);
+    {   // a buffer of this geometry that an earlier model of this process exported: same handle, flags back to epoch 0
+        std::unique_lock<std::mutex> g(g_ipc.mu);
+        for (size_t i = 0; i < g_ipc.idle.size(); ++i) {
+            if (g_ipc.idle[i].dev != device || g_ipc.idle[i].bytes != bytes) continue;
+            const IpcCache::Own o = g_ipc.idle[i];
+            g_ipc.idle.erase(g_ipc.idle.begin() + i);
+            g_ipc.live.push_back(o);
+            g.unlock();
+            CU(cudaSetDevice(device));
+            CU(cudaMemset(o.buf, 0, bytes));
+            CU(cudaDeviceSynchronize());
+            memcpy(ipc_handle64_out, &o.hd, 64);
+            *buf_out = o.buf;
+            return TSC_OK;
+        }
+    }
     unsigned char* buf = nullptr;
     int rc = peer_buffer_alloc(device, n_cols, world, &buf, true);
     if (rc) return rc;
     cudaIpcMemHandle_t hd;
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
     cudaError_t e = cudaIpcGetMemHandle(&hd, buf);
     if (e != cudaSuccess) { cudaFree(buf); return fail(TSC_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
     memcpy(ipc_handle64_out, &hd, 64);
     *buf_out = buf;
+    std::lock_guard<std::mutex> g(g_ipc.mu);
+    g_ipc.live.push_back(IpcCache::Own{device, bytes, buf, hd});
     return TSC_OK;
 }
 
-extern "C" void tsc_peer_buffer_free(void* buf) { if (buf) cudaFree(buf); }
+// An exported buffer goes back to the process's pool (its peers may keep it mapped); anything else is freed.
+static void peer_buffer_release(void* buf) {
+    if (!buf) return;
+    {
+        std::lock_guard<std::mutex> g(g_ipc.mu);
+        for (size_t i = 0; i < g_ipc.live.size(); ++i) {
+            if (g_ipc.live[i].buf != buf) continue;
+            g_ipc.idle.push_back(g_ipc.live[i]);
+            g_ipc.live.erase(g_ipc.live.begin() + i);
+            return;
+        }
+    }
+    dev_free(buf);
+}
+
+extern "C" void tsc_peer_buffer_free(void* buf) { peer_buffer_release(buf); }
 
 // Decide how the shards exchange K-vectors and set it up:
 //   peer  - every GPU maps every rank's exchange buffer (same process: peer access; one process per GPU: CUDA IPC
@@ -684,12 +734,20 @@ static int setup_transport(tsc_handle* h, const tsc_config& cfg) {
                     cudaIpcMemHandle_t hd;
                     memcpy(&hd, handles.data() + 64 * (size_t)r, 64);
                     void* p = nullptr;
+                    const std::string hkey((const char*)&hd, 64);
+                    {
+                        std::lock_guard<std::mutex> g(g_ipc.mu);
+                        auto it = g_ipc.opened.find(hkey);
+                        if (it != g_ipc.opened.end()) p = it->second;
+                    }
+                    if (p) { s.peer_map[r] = (unsigned char*)p; continue; }
                     e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
                     if (e != cudaSuccess)
                         return bad("cudaIpcOpenMemHandle(rank " + std::to_string(r) + ") -- the peer transport needs every GPU of "
                                    "the node visible to every rank", e);
                     s.peer_map[r] = (unsigned char*)p;
                     s.peer_opened[r] = 1;
+                    { std::lock_guard<std::mutex> g(g_ipc.mu); g_ipc.opened[hkey] = p; }
                 }
                 e = cudaMemcpy(s.peer_ptrs_d, s.peer_map.data(), sizeof(unsigned char*) * h->world, cudaMemcpyHostToDevice);
                 if (e != cudaSuccess) return bad("peer pointer table", e);

@@ -35,6 +35,14 @@ def _nccl_env_tuning():
     os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
 
 
+def trim_memory():
+    """Hand the device memory kept from destroyed models back to the driver (the library keeps a bounded cache of blocks
+    between the models of one process: TELESCOPE_B200_CACHE_GB, default 96, 0 = off)."""
+    lib = _abi.load()
+    lib.tsc_trim_memory.restype = None
+    lib.tsc_trim_memory()
+
+
 class DistInfo(object):
     """How this process takes part in a multi-process run (one process per GPU, e.g. under torchrun).
 

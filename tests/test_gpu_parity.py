@@ -585,6 +585,56 @@ def test_non_default_device_options_give_the_same_answer(kw):
     tl.close()
 
 
+def test_device_blocks_are_reused_by_the_next_model_and_trim_releases_them():
+    """A destroyed model's device blocks serve the next model of the process (no cudaMalloc / cudaFree per model); the
+    results do not depend on where the memory came from, and trim_memory() hands everything back."""
+    import re
+    from telescope_b200.likelihood import trim_memory
+    m = _matrix(N=60000, K=900, avg=20, skew=True, seed=97)
+    opts = Opts(max_iter=6)
+    o = _oracle(m, opts)
+    o.em()
+    trim_memory()
+    hits, calls = [], []
+    for _ in range(3):
+        tl = _tl(m, opts)
+        laps = tl.create_laps
+        mt = re.search(r"driver alloc calls=(\d+) \(([\d.]+) ms\), cache hits=(\d+)", laps)
+        assert mt, laps
+        calls.append(int(mt.group(1))); hits.append(int(mt.group(3)))
+        tl.em()
+        assert rel_err(tl.pi, o.pi) < TIGHT and abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
+        assert np.array_equal(tl.reassign_colsum("exclude"), o.reassign_colsum("exclude"))
+        tl.close()
+    assert hits[0] == 0 or calls[0] > calls[1], "the first model of a trimmed process allocates from the driver"
+    assert hits[1] > 0 and hits[2] >= hits[1] and calls[2] <= 2, (hits, calls)
+    trim_memory()
+    tl = _tl(m, opts)
+    assert "cache hits=0" in tl.create_laps
+    tl.close()
+
+
+@pytest.mark.parametrize("rounds", ["0", "1", "4"])
+def test_measured_repartition_does_not_change_results(rounds, monkeypatch):
+    """k_ell_rebalance only moves the boundaries between the warps' runs of the slice stream: every record is still
+    processed exactly once (pi, lnl and the integer counts agree with the oracle whatever the number of rounds)."""
+    monkeypatch.setenv("TELESCOPE_B200_REBALANCE", rounds)
+    m = _matrix(N=400000, K=3000, avg=20, skew=False, seed=98)
+    opts = Opts(max_iter=8, em_epsilon=-1.0)
+    tl, o = _tl(m, opts), _oracle(m, opts)
+    tl.em(); o.em()
+    assert tl.layout_stats()["stream_ctas"] > 100
+    assert rel_err(tl.pi, o.pi) < TIGHT and rel_err(tl.theta, o.theta) < TIGHT
+    assert abs(tl.lnl - o.lnl) <= TIGHT * abs(o.lnl)
+    tl.em()                                           # a second call starts from the re-partitioned runs
+    o2 = _oracle(m, Opts(max_iter=16, em_epsilon=-1.0)).em()
+    assert rel_err(tl.pi, o2.pi) < TIGHT
+    for method, initial in [("exclude", False), ("all", False), ("conf", False)]:
+        a, b = tl.reassign_colsum(method, 0.9, initial), o2.reassign_colsum(method, 0.9, initial)
+        assert (np.array_equal(a, b) if method != "conf" else rel_err(a, b) < RTOL)
+    tl.close()
+
+
 @pytest.mark.parametrize("thresh", [0.0, 0.3, 0.5, 0.99])
 def test_conf_thresholds(thresh):
     """`conf` keeps every hit with z >= thresh and renormalises the survivors (model.py:854-856): with low thresholds

@@ -16,7 +16,7 @@ from telescope_b200.synthetic import synth_csr                      # noqa: E402
 
 
 class Opts(object):
-    em_epsilon, max_iter, pi_prior, theta_prior = -1.0, 3, 0, 200000
+    em_epsilon, max_iter, pi_prior, theta_prior = -1.0, 6, 0, 200000
 
 
 def main():
@@ -29,7 +29,7 @@ def main():
     ip, ix, raw = synth_csr(a.reads, a.loci, 20, a.skew, 1004)
     m = sp.csr_matrix((raw, ix, ip.astype("int32")), shape=(a.reads, a.loci))
     tl = TelescopeLikelihood(m, Opts, devices=[0], kernel=a.kernel)
-    tl.em()                                     # 3 x (fused [+ residual tiles] + tail) + final lnl
+    tl.em()                                     # 6 x (fused [+ re-partition] [+ residual tiles] + tail) + final lnl
     for name in ("fused", "estep", "lnl", "reassign"):
         print(name, tl.time_pass(name, 1))      # warm-up launch + 1 timed launch each
     print(tl.layout_stats(), tl.lnl)

@@ -6,13 +6,18 @@
 //
 // Layout in HBM, per shard (= one GPU's contiguous block of reads):
 //   q[nnz] fp64, col[nnz] int32 (the caller's locus numbering), indptr[rows+1] int64, wy[rows] fp64 (= w_i * Y_i),
-//   tiles[~nnz/115] 32-byte descriptors of the flat-tile passes; the clustered slice stream + its record index (what
-//   the per-iteration kernel reads) and the residual CSR of the reads outside it; K-length fp64 vectors: pi, theta,
+//   tiles[~nnz/115] 32-byte descriptors of the flat-tile passes (with the clustered stream: built when the posterior
+//   is first exported); the clustered slice stream + its record index (what the per-iteration kernel reads) and the
+//   residual CSR of the reads outside it; K-length fp64 vectors: pi, theta,
 //   pt (= pi*theta), their *_prev twins (the parameters the stored posterior z was computed from, model.py:795),
 //   *_init, pisum0, accumulator replicas; the exchange buffer every rank of the node maps.
 // Per EM iteration and shard: stream kernel (+ flat tiles on the residual front) -> k_tail (replica sum, exchange
 // between the GPUs through peer memory, update, loop control).  The loop runs ahead of the host; convergence is decided
-// on the device and polled through pinned memory.
+// on the device and polled through pinned memory.  The first iterations of a model also time every CTA of the stream
+// kernel and re-partition the stream by the measured time (k_ell_rebalance).
+// Construction: the entry arrays are uploaded in chunks and a second stream runs each chunk's kernels beside the next
+// chunk's copy; device blocks, exchange buffers and IPC mappings of destroyed models are kept for the next model of the
+// process (DevCache, IpcCache).
 #include <algorithm>
 #include <chrono>
 #include <cmath>

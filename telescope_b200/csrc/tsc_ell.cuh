@@ -14,8 +14,9 @@
 //     atomics at all in the loop.  A window block is flushed (16 copies summed in fixed order, one coalesced
 //     RED.ADD.F64 of 32 doubles) only when the sorted stream has moved past it: a few thousand sector REDs per
 //     iteration instead of 5e8.
-// The slice records form one byte stream in HBM; every warp takes one contiguous, byte-balanced run of it (batches of
-// 32 records: one index load per lane).  It asks the TMA
+// The slice records form one byte stream in HBM; every warp takes one contiguous run of it (batches of 32 records: one
+// index load per lane) -- byte-balanced at construction, re-partitioned by measured CTA time after the first iterations
+// (k_ell_rebalance below: the byte-balanced runs end 10 % apart).  It asks the TMA
 // unit to pull each record into L2 several records ahead (cp.async.bulk.prefetch.L2, one instruction per record) and
 // then loads the record's loci / Q straight into registers -- every load of a slice is in flight at once, all of them
 // L2 hits.  (A first version staged the records in a shared-memory ring with cp.async.bulk + mbarrier; ncu showed the

@@ -112,6 +112,14 @@ void tsc_pinned_free(void* p);
  * TELESCOPE_B200_CACHE_GB (default 96, 0 = off) and emptied on its own when an allocation fails.  No counterpart in the
  * reference (numpy frees on garbage collection). */
 void tsc_trim_memory(void);
+/* Host helper of reassign('choose') / Telescope.output_report's init_best_random: n bounded draws of numpy's legacy
+ * global generator, element i uniform in [0, counts[i]), exactly as a sequence of np.random.choice(range(a, b)) calls
+ * consumes it (sparse_plus.py:146-153).  key624 / pos: np.random.get_state()[1:3], updated in place for set_state().
+ * counts[i] <= 1 gives pick 0 and consumes nothing; counts must be below 2^31.  No device involved. */
+int tsc_mt19937_draw_picks(uint32_t* key624, int32_t* pos, const int64_t* counts, int64_t n, int32_t* picks);
+/* the same over a per-read array of best-hit counts (tsc_reassign_nbest / tsc_report): reads with at most one best hit get
+ * pick 0 and consume nothing, so the stream equals the reference's loop over the tie reads only */
+int tsc_mt19937_draw_rows(uint32_t* key624, int32_t* pos, const int32_t* nbest, int64_t n, int32_t* picks);
 
 /*
  * TelescopeLikelihood.__init__ (model.py:635-700).

@@ -23,7 +23,7 @@ SYMBOLS = (
     "tsc_config_default", "tsc_create", "tsc_destroy", "tsc_get_constants", "tsc_get_row_info", "tsc_get_q",
     "tsc_em", "tsc_get_kernel_times", "tsc_get_counters", "tsc_get_params", "tsc_set_params", "tsc_estep",
     "tsc_mstep", "tsc_calculate_lnl", "tsc_get_z", "tsc_reassign_nbest", "tsc_reassign_colsum",
-    "tsc_reassign_data", "tsc_get_em_device_ms", "tsc_pinned_alloc", "tsc_pinned_free", "tsc_time_pass", "tsc_allreduce_f64", "tsc_create_laps", "tsc_report", "tsc_choose_ties_colsum", "tsc_get_layout_stats", "tsc_peer_buffer_create", "tsc_peer_buffer_free", "tsc_get_transport", "tsc_get_tail_times", "tsc_trim_memory",
+    "tsc_reassign_data", "tsc_get_em_device_ms", "tsc_pinned_alloc", "tsc_pinned_free", "tsc_time_pass", "tsc_allreduce_f64", "tsc_create_laps", "tsc_report", "tsc_choose_ties_colsum", "tsc_get_layout_stats", "tsc_peer_buffer_create", "tsc_peer_buffer_free", "tsc_get_transport", "tsc_get_tail_times", "tsc_trim_memory", "tsc_mt19937_draw_picks", "tsc_mt19937_draw_rows",
 )
 
 

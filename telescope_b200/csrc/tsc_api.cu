@@ -2483,6 +2483,65 @@ extern "C" int tsc_choose_ties_colsum(tsc_handle* h, int32_t initial, const int3
     return get_kvec(h, s0, s0.colsum, colsum);
 }
 
+// ------------------------------------------------------------------------------------------------- host RNG (choose)
+// reassign('choose') breaks ties with np.random.choice(range(a, b)) per read, in read order (sparse_plus.py:146-153), i.e.
+// one bounded draw of numpy's legacy global generator each: MT19937 words, masked with the smallest 2^k - 1 >= n - 1 and
+// rejected while above n - 1.  The draws are the reference's contract (same seed -> same assignments), and 25 M of them
+// through numpy's array path were two thirds of the one-pass report's wall time; this walks the same generator state in C.
+// key624 / pos are RandomState.get_state()'s; both are updated for set_state().  Host code only, no device involved.
+template <typename CountT>
+static int mt19937_draw(uint32_t* key624, int32_t* pos, const CountT* counts, int64_t n, int32_t* picks) {
+    if (!key624 || !pos || (n > 0 && (!counts || !picks))) return fail(TSC_ERR_ARG, "NULL argument");
+    if (*pos < 0 || *pos > 624) return fail(TSC_ERR_ARG, "MT19937 position out of range");
+    constexpr int N = 624, M = 397;
+    constexpr uint32_t kMatrixA = 0x9908b0dfu, kUpper = 0x80000000u, kLower = 0x7fffffffu;
+    int p = *pos;
+    auto regenerate = [&]() {
+        int k = 0;
+        uint32_t y;
+        for (; k < N - M; ++k) {
+            y = (key624[k] & kUpper) | (key624[k + 1] & kLower);
+            key624[k] = key624[k + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & kMatrixA);
+        }
+        for (; k < N - 1; ++k) {
+            y = (key624[k] & kUpper) | (key624[k + 1] & kLower);
+            key624[k] = key624[k + (M - N)] ^ (y >> 1) ^ ((0u - (y & 1u)) & kMatrixA);
+        }
+        y = (key624[N - 1] & kUpper) | (key624[0] & kLower);
+        key624[N - 1] = key624[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & kMatrixA);
+        p = 0;
+    };
+    auto next32 = [&]() -> uint32_t {
+        if (p == N) regenerate();
+        uint32_t y = key624[p++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        const long long c = (long long)counts[i];
+        if (c <= 1) { picks[i] = 0; continue; }                 // nothing to choose: consumes nothing (like numpy for n = 1)
+        if (c > 0x7fffffffLL) { *pos = p; return fail(TSC_ERR_ARG, "counts must be below 2^31"); }
+        const uint32_t rng = (uint32_t)(c - 1);
+        uint32_t mask = rng;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        uint32_t v;
+        do { v = next32() & mask; } while (v > rng);
+        picks[i] = (int32_t)v;
+    }
+    *pos = p;
+    return TSC_OK;
+}
+
+extern "C" int tsc_mt19937_draw_picks(uint32_t* key624, int32_t* pos, const int64_t* counts, int64_t n, int32_t* picks) {
+    return mt19937_draw<int64_t>(key624, pos, counts, n, picks);
+}
+extern "C" int tsc_mt19937_draw_rows(uint32_t* key624, int32_t* pos, const int32_t* nbest, int64_t n, int32_t* picks) {
+    return mt19937_draw<int32_t>(key624, pos, nbest, n, picks);
+}
+
 extern "C" int tsc_reassign_nbest(tsc_handle* h, int32_t initial, int32_t* nbest_rows) {
     if (!h || !nbest_rows) return fail(TSC_ERR_ARG, "NULL argument");
     return reassign_impl(h, TSC_EXCLUDE, 0.0, initial, nullptr, nbest_rows, nullptr, nullptr);

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _abi
 from .sparse_plus import csr_matrix_plus as csr_matrix
-from .sparse_plus import draw_picks
+from .sparse_plus import draw_picks, draw_row_picks          # noqa: F401
 
 _INT_DTYPE = {"exclude": np.int8, "choose": np.int8, "unique": np.uint8, "all": np.uint8}
 
@@ -370,10 +370,7 @@ class TelescopeLikelihood(object):
             return None
         nbest = np.zeros(self.N, dtype=np.int32)
         _abi.check(self._lib.tsc_reassign_nbest(self._h, 1 if initial else 0, _abi._p(nbest, C.c_int32)))
-        picks = np.zeros(self.N, dtype=np.int32)
-        ties = np.flatnonzero(nbest > 1)
-        picks[ties] = draw_picks(nbest[ties])
-        return picks
+        return draw_row_picks(nbest)
 
     def reassign(self, method, thresh=0.9, initial=False):
         """Assignment matrix, as the reference returns it (int8 / uint8 / float64 csr_matrix)."""
@@ -401,11 +398,9 @@ class TelescopeLikelihood(object):
         out = out.reshape(6, K)
 
         def ties(nbest, initial):
-            picks = np.zeros(N, dtype=np.int32)
-            t = np.flatnonzero(nbest > 1)
-            picks[t] = draw_picks(nbest[t])
+            picks = draw_row_picks(nbest)
             extra = np.zeros(K)
-            if t.size:
+            if nbest.size and int(nbest.max()) > 1:
                 _abi.check(self._lib.tsc_choose_ties_colsum(self._h, 1 if initial else 0, _abi._p(nbest, C.c_int32),
                                                             _abi._p(picks, C.c_int32), _abi._p(extra, C.c_double)))
             return extra

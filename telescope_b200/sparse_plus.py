@@ -103,5 +103,55 @@ def draw_picks(counts):
     if counts.size == 0:
         return counts.copy()
     # np.random.choice(range(a, b)) is one bounded draw randint(0, b-a); randint with an array of bounds walks the
-    # same generator state element by element (checked in tests/test_host.py against the sequential form).
+    # same generator state element by element (checked in tests/test_host.py against the sequential form).  For long
+    # arrays (25 M tie reads at 50 M reads) the library walks the same MT19937 state in C, ~5x faster.
+    if counts.size >= 4096:
+        picks = _draw_native(counts, rows=False)
+        if picks is not None:
+            return picks
     return np.random.randint(0, counts)
+
+
+def draw_row_picks(nbest):
+    """Tie-breaks of reassign('choose') for every read at once: `nbest` holds the number of best hits per read; reads
+    with more than one get a draw in [0, nbest), in read order -- the draws `draw_picks(nbest[nbest > 1])` makes, without
+    the gather / scatter through the index of the tie reads -- the others get 0 and consume nothing.  int32 array."""
+    nbest = np.ascontiguousarray(nbest, dtype=np.int32)
+    if nbest.size >= 4096:
+        picks = _draw_native(nbest, rows=True)
+        if picks is not None:
+            return picks
+    picks = np.zeros(nbest.size, dtype=np.int32)
+    t = np.flatnonzero(nbest > 1)
+    if t.size:
+        picks[t] = np.random.randint(0, nbest[t].astype(np.int64))
+    return picks
+
+
+def _draw_native(counts, rows):
+    """tsc_mt19937_draw_picks / _rows on numpy's global legacy generator (stream-identical to np.random.randint with an
+    array of bounds, tests/test_host.py); None when the library or the generator state is not usable."""
+    import ctypes as C
+    try:
+        from . import _abi
+        lib = _abi.load()
+        fn = lib.tsc_mt19937_draw_rows if rows else lib.tsc_mt19937_draw_picks
+    except Exception:
+        return None
+    st = np.random.get_state()
+    if st[0] != 'MT19937':
+        return None
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = C.c_int32(int(st[2]))
+    ctype, dtype = (C.c_int32, np.int32) if rows else (C.c_int64, np.int64)
+    counts = np.ascontiguousarray(counts, dtype=dtype)
+    if not rows and counts.size and counts.min() < 1:
+        return None                                   # numpy raises for an empty range: let it
+    picks = np.empty(counts.size, dtype=np.int32)
+    fn.restype = C.c_int
+    rc = fn(key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(pos), counts.ctypes.data_as(C.POINTER(ctype)),
+            C.c_int64(counts.size), picks.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        return None                                   # (a bound of 2^31 or more: numpy's own path handles it)
+    np.random.set_state(('MT19937', key, pos.value, st[3], st[4]))
+    return picks

@@ -69,6 +69,56 @@ def test_csr_matrix_plus_known_answers():
         assert m.check_equal(C.load(os.path.join(d, "m.npz")))
 
 
+@pytest.mark.parametrize("n,lo,hi", [(5000, 2, 5), (70001, 1, 40), (8192, 2, 3), (20000, 2, 2 ** 31 - 1), (4096, 3, 4),
+                                     (300, 2, 9)])
+def test_native_tie_draws_walk_numpys_generator(n, lo, hi):
+    """tsc_mt19937_draw_picks / _rows (host code of the library, used for long arrays) give the draws of
+    np.random.randint(0, counts) -- i.e. of the reference's np.random.choice(range(a, b)) per tie read,
+    sparse_plus.py:146-153 -- and leave the global generator in the same state (next uniform and normal draws agree)."""
+    from telescope_b200.sparse_plus import draw_picks, draw_row_picks
+    counts = np.random.default_rng(n).integers(lo, hi, size=n)
+    np.random.seed(1000 + n)
+    want = np.random.randint(0, counts)
+    after_want = (np.random.random(4), np.random.standard_normal(3), np.random.randint(0, 1000, 5))
+    np.random.seed(1000 + n)
+    got = draw_picks(counts)
+    after_got = (np.random.random(4), np.random.standard_normal(3), np.random.randint(0, 1000, 5))
+    assert np.array_equal(got, want)
+    assert all(np.array_equal(a, b) for a, b in zip(after_got, after_want))
+    if hi < 2 ** 20:
+        # per-read form: reads with 0 or 1 best hits in between consume nothing and pick 0
+        nbest = np.zeros(3 * n, dtype=np.int32)
+        where = np.sort(np.random.default_rng(n + 1).choice(3 * n, size=n, replace=False))
+        nbest[where] = counts
+        nbest[(where[::7] + 1) % (3 * n)] = np.where(nbest[(where[::7] + 1) % (3 * n)] == 0, 1, nbest[(where[::7] + 1) % (3 * n)])
+        ties = np.flatnonzero(nbest > 1)
+        np.random.seed(77)
+        want_rows = np.zeros(3 * n, dtype=np.int64)
+        want_rows[ties] = np.random.randint(0, nbest[ties].astype(np.int64))
+        nxt_want = np.random.random(2)
+        np.random.seed(77)
+        got_rows = draw_row_picks(nbest)
+        nxt_got = np.random.random(2)
+        assert got_rows.dtype == np.int32 and np.array_equal(got_rows, want_rows) and np.array_equal(nxt_got, nxt_want)
+
+
+def test_native_tie_draws_after_a_partial_block_and_across_regenerations():
+    """The generator position is honoured: draws that start in the middle of a 624-word block and run over several
+    regenerations continue numpy's sequence."""
+    from telescope_b200.sparse_plus import draw_picks
+    counts = np.full(10000, 3)                       # 25 % rejections: ~13 300 words, 21 regenerations
+    for burn in (0, 1, 311, 623, 624, 625):
+        np.random.seed(9)
+        np.random.randint(0, 2 ** 31 - 1, burn)      # one word each
+        want = np.random.randint(0, counts)
+        tail_want = np.random.randint(0, 10 ** 6, 3)
+        np.random.seed(9)
+        np.random.randint(0, 2 ** 31 - 1, burn)
+        got = draw_picks(counts)
+        tail_got = np.random.randint(0, 10 ** 6, 3)
+        assert np.array_equal(got, want) and np.array_equal(tail_got, tail_want), burn
+
+
 def test_choose_random_consumes_rng_like_reference_loop():
     from telescope_b200.sparse_plus import csr_matrix_plus as C
     from telescope_b200.sparse_plus import draw_picks

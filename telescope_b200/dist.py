@@ -70,7 +70,7 @@ def allgather(tag, payload=b"", timeout=600.0):
     with open(tmp, "wb") as fh:
         fh.write(payload)
     os.replace(tmp, base + str(rank))            # atomic: a reader sees the whole blob or nothing
-    out, t0 = [None] * world, time.time()
+    out, t0, polls = [None] * world, time.time(), 0
     while True:
         for r in range(world):
             if out[r] is None:
@@ -84,7 +84,9 @@ def allgather(tag, payload=b"", timeout=600.0):
         if time.time() - t0 > timeout:
             missing = [r for r in range(world) if out[r] is None]
             raise RuntimeError("rank %d: no %r blob from ranks %s after %.0f s" % (rank, tag, missing, timeout))
-        time.sleep(0.002)
+        polls += 1
+        if polls > 400:                  # ranks of one launch arrive within a millisecond or two of each other: look again
+            time.sleep(0.0005)           # at once for a while before yielding the core between looks
 
 
 def rendezvous(timeout=600.0, transport="peer"):

@@ -14,6 +14,9 @@ stopping early, exactly as on the CPU arm.
              resident in HBM.  Like the reference's em(), the call ends with one calculate_lnl pass (model.py:800-801).
   e2e      = K / wall time of the whole job through the public class with HOST (pinned) CSR buffers:
              TelescopeLikelihood(csr, opts) [H2D of the CSR, Q build, clustering] + em(K) + D2H of pi/theta.
+             Three such jobs run back to back, each on a fresh model; the line reports the median and lists all
+             three (`runs`, `runs_laps_ms`): the first job of a process allocates its device memory (and the staging
+             pool / IPC mappings) from the driver, later ones reuse the blocks the destroyed model handed back.
              e2e_pageable = the same from ordinary (pageable) numpy/scipy arrays, e2e_report = e2e plus the one-pass
              output_report column sums (model.py:432-458).
   roofline = the fused E+M kernel(s) of one iteration: ALGORITHMIC bytes nnz*12 + (N+1)*4 / mean
